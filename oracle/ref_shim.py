@@ -1,0 +1,123 @@
+"""Import the UNMODIFIED reference modules (cshizhe/VLN-HAMT) under torch 2.11 / transformers 5.x.
+
+TEST INFRASTRUCTURE ONLY.  Works only where the reference checkout exists (this build container:
+/root/reference).  It never exists on the GPU box; everything that runs there uses the committed
+golden vectors produced through this shim by oracle/make_golden.py.
+
+The shim follows SURVEY.md section 8c: the reference pins transformers==4.12.3
+(requirements.txt:11) and uses three things from it that transformers 5 removed/changed:
+  * transformers.modeling_utils.get_parameter_device            (vilmodel.py:16)
+  * BertPreTrainedModel.init_weights / _tie_or_clone_weights    (vilmodel.py:589, pretrain_cmt.py:93-99)
+  * from_pretrained(None, config=..., state_dict=...)           (main_r2r.py:146-148)
+None of these contributes forward arithmetic.  No reference file is edited or copied.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get("HAMT_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "pretrain_src", "model", "vilmodel.py"))
+
+
+class _CompatBertPreTrainedModel(nn.Module):
+    """Stands in for transformers==4.12.3 BertPreTrainedModel (init / tying / (de)serialisation only)."""
+    base_model_prefix = "bert"
+
+    def __init__(self, config, *a, **k):
+        super().__init__()
+        self.config = config
+
+    def _init_weights(self, mod):
+        if isinstance(mod, (nn.Linear, nn.Embedding)):
+            mod.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(mod, nn.LayerNorm):
+            mod.bias.data.zero_()
+            mod.weight.data.fill_(1.0)
+        if isinstance(mod, nn.Linear) and mod.bias is not None:
+            mod.bias.data.zero_()
+
+    def init_weights(self):
+        self.apply(self._init_weights)
+
+    def _tie_or_clone_weights(self, a, b):
+        a.weight = b.weight
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path=None, config=None, state_dict=None, **kw):
+        model = cls(config)
+        if state_dict:
+            model.load_state_dict(state_dict, strict=False)
+        return model
+
+
+_LOADED = {}
+
+
+def _patch_transformers():
+    import transformers
+    import transformers.modeling_utils as mu
+    mu.get_parameter_device = lambda m: next(m.parameters()).device
+    transformers.BertPreTrainedModel = _CompatBertPreTrainedModel
+
+
+def _import_from(subdir: str, modname: str):
+    """Import `modname` with <reference>/<subdir> at the front of sys.path, isolated from the other
+    tree (pretrain_src and finetune_src both have top-level packages named `utils`)."""
+    key = (subdir, modname)
+    if key in _LOADED:
+        return _LOADED[key]
+    if not reference_available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+    _patch_transformers()
+    sys.dont_write_bytecode = True          # /root/reference is read-only
+    path = os.path.join(REFERENCE_ROOT, subdir)
+    # purge clashing top-level packages from a previous import of the other tree
+    for name in list(sys.modules):
+        if name.split(".")[0] in ("model", "models", "utils", "data", "optim"):
+            f = getattr(sys.modules[name], "__file__", "") or ""
+            if REFERENCE_ROOT in f and path not in f:
+                del sys.modules[name]
+    sys.path.insert(0, path)
+    try:
+        mod = importlib.import_module(modname)
+    finally:
+        sys.path.remove(path)
+    _LOADED[key] = mod
+    return mod
+
+
+def pretrain_config(tasks=("mlm", "sap", "sar", "sprel", "mrc", "itm"), config_name="r2r_model_config.json", **overrides):
+    from transformers import PretrainedConfig
+    cfg = PretrainedConfig.from_json_file(os.path.join(REFERENCE_ROOT, "pretrain_src", "config", config_name))
+    cfg.pretrain_tasks = set(tasks)                 # main_r2r.py:123-126
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def load_pretrain_model(cfg):
+    """-> reference MultiStepNavCMTPreTraining (pretrain_src/model/pretrain_cmt.py:73)."""
+    mod = _import_from("pretrain_src", "model.pretrain_cmt")
+    return mod.MultiStepNavCMTPreTraining(cfg)
+
+
+def load_navcmt(cfg):
+    """-> reference NavCMT (finetune_src/models/vilmodel_cmt.py:610)."""
+    mod = _import_from("finetune_src", "models.vilmodel_cmt")
+    return mod.NavCMT(cfg)
