@@ -1,0 +1,120 @@
+/* hamt_b200.h -- C ABI of libhamt_b200.so: the sm_100a kernels behind the HAMT hot path.
+ *
+ * The reference (cshizhe/VLN-HAMT) has no native code and no FFI; its hot path is the
+ * torch-eager op sequence of pretrain_src/model/vilmodel.py / pretrain_cmt.py and
+ * finetune_src/models/vilmodel_cmt.py.  Each entry point below replaces one group of those eager ops
+ * (cited per function).  The drop-in boundary a reference maintainer binds to is this header; the
+ * ctypes binding used by this repo is vln-hamt_b200/_lib.py and the module-level mirror of the
+ * reference API is vln-hamt_b200/{vilmodel,pretrain_cmt,vilmodel_cmt,model_HAMT}.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator); kernels never allocate;
+ *  - activations are bf16 row-major, parameters / statistics / gradients of parameters are fp32;
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *  - return 0 on success, negative on invalid arguments or launch failure; hamt_last_error() gives the
+ *    text (thread-local);  no C++ exceptions cross the boundary;
+ *  - dropout: `seed_ptr` -> one uint64 in device memory (so captured CUDA graphs can be replayed with a
+ *    fresh seed), `site` = unique id of the call site within a step, `p` = drop probability (0 = off).
+ *    Forward and backward regenerate the identical mask from (seed, site, element index).
+ */
+#ifndef HAMT_B200_H
+#define HAMT_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAMT_ABI_VERSION 1
+
+int hamt_abi_version(void);
+const char* hamt_last_error(void);
+/* number of kernels launched by this library in the calling process (bench.py gpu_launches) */
+long long hamt_launch_count(void);
+
+/* D[M,N] = act(alpha * sum_k A(m,k) B(n,k) + bias[n])   tcgen05 GEMM, bf16 in, fp32 accumulate.
+ * a_mn = 0: A stored [M,K] (pitch lda); 1: A stored [K,M].  b_mn likewise for B ([N,K] / [K,N]).
+ *   forward  y = x W^T           : A = x (a_mn 0), B = W [N,K] (b_mn 0)          vilmodel.py:96-98,140,169,182
+ *   dgrad    dx = dy W           : A = dy (a_mn 0), B = W [N,K] read as [K=N,N=K] (b_mn 1)
+ *   wgrad    dW = dy^T x         : A = dy (a_mn 1), B = x (b_mn 1), fp32 out, out_mode 2
+ * out_f32: 0 bf16 / 1 fp32 output.  out_mode: 0 store, 1 out += , 2 out += with split-K atomics.
+ * act: 0 none, 1 exact-erf GELU (vilmodel.py:23-29), 2 ReLU (pretrain_cmt.py:16).
+ * aux_mode: 0 none, 1 also store the pre-activation (bf16) to aux, 2 multiply by dGELU(aux), 3 by (aux > 0).
+ * tile_n: 0 auto / 128 / 256.  splits: 0 auto. */
+int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out, long long ldo, int out_f32,
+                   int out_mode, int M, int N, int K, const float* bias, int act, int aux_mode, void* aux, long long ld_aux, float alpha,
+                   int tile_n, int splits, void* stream);
+
+/* y = LayerNorm(dropout(x) + res) ; BertSelfOutput / BertOutput tail (vilmodel.py:139-143,181-185).
+ * z_out (may alias x, may be null) receives dropout(x)+res in bf16; mean/rstd fp32 [M] (may be null). */
+int hamt_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd, int M,
+                int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+/* backward: dx (grad of x, dropout applied; null to skip), dres = dz + dres_in (null to skip); dgamma/dbeta/dbias
+ * (column sums, fp32) are ACCUMULATED into; any may be null. */
+int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
+                float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site, float p,
+                void* stream);
+
+/* fused attention, head_dim 64: out = dropout(softmax(q k^T * scale + mask)) v ; vilmodel.py:96-129 (self), :322-349 (cross).
+ * element (b,s,h,d) of q at q + b*q_bstride + s*ldq + h*64 + d (same for k/v with kv strides, out with o strides).
+ * mask: additive fp32 [B,Sk] (the reference's (1-m)*-10000 row) or null.  lse: fp32 [B,heads,Sq] (needed for backward). */
+int hamt_attn_fwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,
+                  const float* mask, void* out, long long ldo, long long o_bstride, float* lse, int B, int heads, int Sq, int Sk, float scale,
+                  const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+/* backward; dq/dk/dv use the q/k/v strides.  Sq, Sk <= 128 in this version. */
+int hamt_attn_bwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,
+                  const float* mask, const void* out, long long ldo, long long o_bstride, const float* lse, const void* dout, long long lddo,
+                  long long do_bstride, void* dq, void* dk, void* dv, int B, int heads, int Sq, int Sk, float scale,
+                  const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+
+/* BertEmbeddings (vilmodel.py:54-69): out = dropout(LN(word[ids] + pos[s] + type0)), ids int64 [B,L]. */
+int hamt_embed_text_fwd(const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma, const float* beta,
+                        void* out, int B, int L, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+int hamt_embed_text_bwd(const void* dy, const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                        float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta, int B, int L, int H, float eps,
+                        const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+
+/* ImageEmbeddings / HistoryEmbeddings / pano-token embedding (vilmodel.py:496-505, :549-571):
+ *   s = LN_img(t) + LN_ang(ang W_ang^T + b_ang) [+ add_vec] [+ nav_table[nav_ids]] [+ extra] [+ pos_table[pos]]
+ *   out = dropout(g_f ? LN_f(s) : s)
+ * t = img_linear(x) (bf16 [M,H], from hamt_gemm_bf16).  pos of row r = pos_ids ? pos_ids[r] : r % pos_mod. */
+typedef struct {
+  const void* t; const float* ang; int A;
+  const float* w_ang; const float* b_ang; const float* g_img; const float* b_img; const float* g_ang; const float* be_ang;
+  const float* add_vec; const float* nav_table; const long long* nav_ids; const float* extra;
+  const float* pos_table; const long long* pos_ids; int pos_mod;
+  const float* g_f; const float* b_f;
+  void* out; int M; int H; float eps;
+  const unsigned long long* seed_ptr; unsigned int site; float p;
+} hamt_embed_feat_desc;
+typedef struct {
+  const void* dy; void* dt;
+  float* dw_ang; float* db_ang; float* dg_img; float* db_img; float* dg_ang; float* dbe_ang; float* dadd_vec; float* dnav_table;
+  float* dextra; float* dpos_table; float* dg_f; float* db_f; float* db_lin;
+} hamt_embed_feat_grads;
+int hamt_embed_feat_fwd(const hamt_embed_feat_desc* d, void* stream);
+int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_grads* g, void* stream);
+
+/* streaming helpers */
+int hamt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);
+int hamt_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream);      /* out[n] += sum_m x[m,n] (bias grads) */
+int hamt_mean_pool_fwd(const void* x, float* out, int N, int P, int H, void* stream);            /* torch.mean(dim=2), vilmodel.py:563-564 */
+int hamt_mean_pool_bwd(const float* dy, void* dx, int N, int P, int H, void* stream);
+int hamt_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int hamt_mul_rows_bf16(const void* a, const void* v, void* out, int B, int S, int H, void* stream); /* ob * txt[:, :1], pretrain_cmt.py:176 */
+
+/* proxy-task head pieces (pretrain_src/model/pretrain_cmt.py)
+ * rowdot: final Linear(H -> N<=4) of the SAP/SAR/SPREL/ITM heads (:13-47,:62-71): y fp32 [M,N] = x(bf16 [M,H]) w^T(fp32 [N,H]) + b;
+ * backward: dx bf16 (null to skip), dw/db accumulated.  ce: F.cross_entropy(reduction='none') over fp32 logits with -inf entries
+ * allowed (:150-153,:177-180,:254-259); ce_bwd writes gloss[m]*(softmax - onehot) as fp32 [M,N] (pitch ld_d) or as bf16 padded to
+ * pitch ld_d (zeros beyond N) ready to be a TMA GEMM operand.  gather/scatter: hidden[mask] rows (:161-165). */
+int hamt_rowdot_fwd(const void* x, const float* w, const float* b, float* y, int M, int N, int H, void* stream);
+int hamt_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* db, int M, int N, int H, void* stream);
+int hamt_ce_fwd(const float* logits, long long ld, const long long* labels, float* loss, float* lse, int M, int N, void* stream);
+int hamt_ce_bwd(const float* logits, long long ld, const long long* labels, const float* lse, const float* gloss, float* dl_f32, void* dl_bf16,
+                long long ld_d, int M, int N, void* stream);
+int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);   /* out[i] = x[idx[i]] */
+int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);  /* out[idx[i]] = x[i] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAMT_B200_H */

@@ -1,0 +1,110 @@
+"""Fused attention forward / backward parity against an fp32 torch restatement of
+BertSelfAttention / BertOutAttention (pretrain_src/model/vilmodel.py:96-129, :322-349): scores / sqrt(d) THEN + mask,
+softmax, (dropout), P V.  Q/K/V are read in place from a fused [tokens, 3*768] projection buffer."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HEADS, D = 12, 64
+
+
+def _ops():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import ops
+    return ops
+
+
+def _ref(q, k, v, mask, B, Sq, Sk):
+    qh = q.float().view(B, Sq, HEADS, D).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Sk, HEADS, D).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Sk, HEADS, D).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(D)
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    p = torch.softmax(s, -1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(B * Sq, HEADS * D), p
+
+
+@pytest.mark.parametrize("B,Sq,Sk,masked", [(3, 36, 36, False), (4, 80, 80, True), (4, 80, 53, True), (4, 53, 80, True), (2, 16, 5, True),
+                                             (2, 1, 17, True), (2, 128, 128, True), (5, 17, 100, True)])
+def test_attention_fwd_bwd(B, Sq, Sk, masked):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + Sq * 10 + Sk)
+    self_attn = Sq == Sk
+    if self_attn:
+        qkv = torch.randn(B * Sq, 3 * HEADS * D, generator=g).to(torch.bfloat16).cuda()
+        q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    else:
+        qb = torch.randn(B * Sq, 3 * HEADS * D, generator=g).to(torch.bfloat16).cuda()
+        kb = torch.randn(B * Sk, 3 * HEADS * D, generator=g).to(torch.bfloat16).cuda()
+        q, k, v = qb[:, :768], kb[:, 768:1536], kb[:, 1536:]
+    mask = None
+    if masked:
+        lens = torch.randint(1, Sk + 1, (B,), generator=g)
+        lens[0] = Sk
+        mask = ((torch.arange(Sk)[None] >= lens[:, None]).float() * -10000.0).cuda()
+    out, lse = ops.attn_fwd(q, k, v, B, Sq, Sk, HEADS, mask)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref, p = _ref(qr, kr, vr, mask, B, Sq, Sk)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, f"fwd err {err}"
+    dout = torch.randn(B * Sq, HEADS * D, generator=g).to(torch.bfloat16).cuda()
+    ref.backward(dout.float())
+    if self_attn:
+        dqkv = torch.zeros_like(qkv)
+        dq, dk, dv = dqkv[:, :768], dqkv[:, 768:1536], dqkv[:, 1536:]
+    else:
+        dqb, dkb = torch.zeros_like(qb), torch.zeros_like(kb)
+        dq, dk, dv = dqb[:, :768], dkb[:, 768:1536], dkb[:, 1536:]
+    ops.attn_bwd(q, k, v, out, lse, dout, dq, dk, dv, B, Sq, Sk, HEADS, mask)
+    for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
+        e = (got.float() - want).abs().max().item()
+        assert e < 4e-2 * max(1.0, want.abs().max().item()), f"{name} err {e}"
+
+
+def test_attention_fully_masked_rows_match_reference():
+    """-10000 masks (not -inf): a fully masked key row still yields the reference's softmax over the raw scores."""
+    ops = _ops()
+    B, S = 2, 20
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B * S, 2304, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.full((B, S), -10000.0).cuda()
+    out, _ = ops.attn_fwd(qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:], B, S, S, HEADS, mask)
+    ref, _ = _ref(qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:], mask, B, S, S)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_attention_dropout_statistics_and_backward_consistency():
+    """With V = identity-like probes the output exposes dropout(P); check keep-rate and that the backward
+    (which regenerates the mask) matches autograd through the explicitly recovered mask."""
+    ops = _ops()
+    B, S, p = 2, 64, 0.1
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(B * S, 2304, generator=g).to(torch.bfloat16).cuda() * 0.5
+    eye = torch.eye(S, D).to(torch.bfloat16).cuda()           # S == D: V_h = I  ->  out_h = dropout(P_h)
+    qkv[:, 1536:] = eye.repeat(B, HEADS)
+    q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    seed = torch.tensor([99], dtype=torch.int64, device="cuda")
+    drop = ops.Drop(seed, 3, p)
+    out, lse = ops.attn_fwd(q, k, v, B, S, S, HEADS, None, drop)
+    _, P = _ref(q, k, v, None, B, S, S)                       # [B,H,S,S]
+    Pd = out.float().view(B, S, HEADS, D).permute(0, 2, 1, 3)  # dropout(P) (bf16-rounded)
+    keep = Pd > 0
+    big = P > 1e-3
+    frac = keep[big].float().mean().item()
+    assert abs(frac - (1 - p)) < 1e-2, frac
+    assert (Pd[keep & big] / P[keep & big] - 1 / (1 - p)).abs().max().item() < 5e-2
+    # backward with the recovered mask
+    mult = torch.where(keep | ~big, torch.full_like(P, 1 / (1 - p)), torch.zeros_like(P))
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    qh = qr.view(B, S, HEADS, D).permute(0, 2, 1, 3); kh = kr.view(B, S, HEADS, D).permute(0, 2, 1, 3); vh = vr.view(B, S, HEADS, D).permute(0, 2, 1, 3)
+    pr = torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, -1) * mult
+    ref = (pr @ vh).permute(0, 2, 1, 3).reshape(B * S, 768)
+    dout = torch.randn(B * S, 768, generator=g).to(torch.bfloat16).cuda()
+    ref.backward(dout.float())
+    dqkv = torch.zeros_like(qkv)
+    ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:, :768], dqkv[:, 768:1536], dqkv[:, 1536:], B, S, S, HEADS, None, drop)
+    for got, want in ((dqkv[:, :768], qr.grad), (dqkv[:, 768:1536], kr.grad), (dqkv[:, 1536:], vr.grad)):
+        assert (got.float() - want).abs().max().item() < 6e-2 * max(1.0, want.abs().max().item())

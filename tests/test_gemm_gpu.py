@@ -1,0 +1,130 @@
+"""tcgen05 GEMM parity (C-ABI hamt_gemm_bf16 through ops.gemm) against fp32 torch matmul on the same
+bf16-rounded operands.  Covers the three operand-major combinations the hot path uses (forward
+K-major x K-major, dgrad K-major x MN-major, wgrad MN-major x MN-major), both tile widths, ragged
+edges (M, N, K not multiples of the tile), every fused epilogue, and split-K accumulation."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _tol(K):
+    # fp32 accumulation of K bf16 products; output rounded to bf16 -> 2^-8 relative + accumulation noise
+    return 2e-2, 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (5120, 768, 768), (1024, 2304, 768), (640, 3072, 768),
+                                    (333, 1000, 768), (256, 768, 3072), (200, 768, 1000), (77, 37 * 8, 1536)])
+@pytest.mark.parametrize("tile_n", [128, 256])
+def test_gemm_forward_bias(M, N, K, tile_n):
+    ops = _ops()
+    a, b = _rand((M, K), 1), _rand((N, K), 2, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    out = ops.gemm(a, b, bias=bias, tile_n=tile_n)
+    ref = a.float() @ b.float().t() + bias
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, f"max err {err}"
+
+
+def test_gemm_fp32_out_exact_small():
+    """fp32 output, integer-valued operands: the tensor-core result must be exact."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randint(-4, 5, (256, 192), generator=g).to(torch.bfloat16).cuda()
+    b = torch.randint(-4, 5, (384, 192), generator=g).to(torch.bfloat16).cuda()
+    out = ops.gemm(a, b, out_dtype=torch.float32)
+    assert torch.equal(out, a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu"])
+def test_gemm_activation_and_preact(act):
+    ops = _ops()
+    M, N, K = 512, 3072, 768
+    a, b = _rand((M, K), 4), _rand((N, K), 5, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(6)).cuda() * 0.1
+    aux = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU if act == "gelu" else ops.ACT_RELU, aux_mode=ops.AUX_STORE_PRE, aux=aux)
+    pre = a.float() @ b.float().t() + bias
+    ref = torch.nn.functional.gelu(pre) if act == "gelu" else torch.relu(pre)
+    assert (aux.float() - pre).abs().max().item() <= 2e-2 * pre.abs().max().item()
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 768, 768), (300, 768, 3072), (5120, 3072, 768), (129, 768, 1000)])
+def test_gemm_dgrad_mn_major_b(M, N, K):
+    """dx[M,N] = dy[M,K] @ W[K,N]: B operand is MN-major (W stored [K_red, N_out])."""
+    ops = _ops()
+    dy, w = _rand((M, K), 7), _rand((K, N), 8, 0.05)
+    out = ops.gemm(dy, w, b_mn=True)
+    ref = dy.float() @ w.float()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, f"max err {err}"
+
+
+def test_gemm_dgrad_dgelu_epilogue():
+    ops = _ops()
+    M, N, K = 384, 3072, 768
+    dy, w = _rand((M, K), 9), _rand((K, N), 10, 0.05)
+    pre = _rand((M, N), 11)
+    out = ops.gemm(dy, w, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ref = (dy.float() @ w.float()) * x.grad
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("Mred,N,K", [(5120, 768, 768), (3392, 3072, 768), (1000, 768, 3072), (160, 2304, 768), (34560, 768, 768)])
+def test_gemm_wgrad_mn_major_both_splitk(Mred, N, K):
+    """dW[N,K] += dy[Mred,N]^T @ x[Mred,K]: both operands MN-major, fp32 output, split-K atomics."""
+    ops = _ops()
+    dy, x = _rand((Mred, N), 12, 0.1), _rand((Mred, K), 13)
+    out = torch.full((N, K), 0.5, dtype=torch.float32, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, accumulate=True)
+    ref = dy.float().t() @ x.float() + 0.5
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, f"max err {err}"
+
+
+def test_gemm_wgrad_forced_splits_match():
+    ops = _ops()
+    dy, x = _rand((4096, 768), 14, 0.1), _rand((4096, 768), 15)
+    outs = []
+    for s in (1, 4, 16):
+        o = torch.zeros((768, 768), dtype=torch.float32, device="cuda")
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=o, accumulate=True, splits=s)
+        outs.append(o)
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-2
+    assert (outs[0] - outs[2]).abs().max().item() < 1e-2
+
+
+def test_gemm_strided_views():
+    """Operands / outputs that are column slices of wider buffers (fused QKV layout)."""
+    ops = _ops()
+    big = _rand((512, 2304), 16)
+    w = _rand((768, 768), 17, 0.05)
+    a = big[:, 768:1536]
+    outbuf = torch.zeros((512, 2304), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, out=outbuf[:, 1536:])
+    ref = a.float() @ w.float().t()
+    assert (outbuf[:, 1536:].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert outbuf[:, :1536].abs().max().item() == 0
+
+
+def test_gemm_rejects_bad_pitch():
+    ops = _ops()
+    a = _rand((64, 100), 18)[:, :99]          # pitch 100 elements = 200 B: not a multiple of 16 B
+    b = _rand((64, 99), 19)
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.gemm(a, b)

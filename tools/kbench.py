@@ -1,0 +1,66 @@
+"""Kernel micro-benchmarks (CUDA events, warm-up, L2-sized rotation of inputs) -- development aid, not the graded bench."""
+import json
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import hamt_b200  # noqa
+from hamt_b200 import ops
+
+
+def timeit(fn, n=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+
+def main():
+    res = []
+    for (M, N, K) in [(34560, 768, 768), (34560, 2304, 768), (34560, 3072, 768), (34560, 768, 3072), (5120, 768, 768), (5120, 2304, 768),
+                      (5120, 3072, 768), (5120, 768, 3072), (8512, 2304, 768), (3392, 3072, 768)]:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        row = {"M": M, "N": N, "K": K}
+        for tn in (128, 256):
+            t = timeit(lambda: ops.gemm(a, w, bias=bias, tile_n=tn))
+            row[f"fwd_tn{tn}_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        t = timeit(lambda: torch.nn.functional.linear(a, w, bias.to(torch.bfloat16)))
+        row["torch_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        dy = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+        t = timeit(lambda: ops.gemm(dy, w, b_mn=True))
+        row["dgrad_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        g = torch.zeros(N, K, device="cuda")
+        t = timeit(lambda: ops.gemm(dy, a, a_mn=True, b_mn=True, out=g, accumulate=True))
+        row["wgrad_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        res.append(row)
+        print(json.dumps(row), flush=True)
+    # attention
+    for (B, Sq, Sk) in [(960, 36, 36), (64, 80, 80), (64, 80, 53), (64, 53, 80), (64, 53, 53)]:
+        qkv = torch.randn(B * max(Sq, Sk), 2304, device="cuda").to(torch.bfloat16)
+        q, k, v = qkv[:B * Sq, :768], qkv[:B * Sk, 768:1536], qkv[:B * Sk, 1536:]
+        t = timeit(lambda: ops.attn_fwd(q, k, v, B, Sq, Sk, 12, None))
+        out, lse = ops.attn_fwd(q, k, v, B, Sq, Sk, 12, None)
+        dout = torch.randn_like(out)
+        dqkv = torch.zeros_like(qkv)
+        t2 = timeit(lambda: ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:B * Sq, :768], dqkv[:B * Sk, 768:1536], dqkv[:B * Sk, 1536:], B, Sq, Sk, 12, None))
+        print(json.dumps({"attn": [B, Sq, Sk], "fwd_us": round(t * 1e3, 1), "bwd_us": round(t2 * 1e3, 1),
+                          "fwd_GBs": round((B * (Sq + 2 * Sk) * 768 * 2 + B * Sq * 768 * 2) / t / 1e6, 1)}), flush=True)
+    # layernorm
+    for M in (34560, 5120):
+        x = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+        r = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+        gm, bt = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
+        t = timeit(lambda: ops.ln_fwd(x, r, gm, bt, 1e-12))
+        print(json.dumps({"ln_fwd_M": M, "us": round(t * 1e3, 1), "GBs": round(M * 768 * 2 * 4 / t / 1e6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

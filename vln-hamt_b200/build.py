@@ -1,0 +1,75 @@
+"""Build libhamt_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Explicit `nvcc -shared` -- no torch.utils.cpp_extension, no JIT cache: the .so lands next to the
+sources (vln-hamt_b200/csrc/libhamt_b200.so) so it travels with the repo snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libhamt_b200.so")
+SOURCES = ["hamt_abi.cu", "hamt_gemm.cu", "hamt_ln.cu", "hamt_attn.cu", "hamt_embed.cu", "hamt_heads.cu"]
+HEADERS = ["hamt_common.cuh", "hamt_kernels.h", os.path.join("..", "..", "include", "hamt_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isfile(cand) or cand == "nvcc"):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p):
+            with open(p, "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    stamp = LIB + ".sha256"
+    dig = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+    srcs = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append(f"=== {s} ===\n{out}")
+        if p.returncode != 0:
+            failed = True
+    with open(os.path.join(CSRC, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if failed:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("nvcc failed (see vln-hamt_b200/csrc/build.log)")
+    if verbose:
+        print("\n".join(log))
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

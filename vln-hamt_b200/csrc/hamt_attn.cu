@@ -1,0 +1,383 @@
+// Fused multi-head attention forward / backward for the HAMT hot path (head_dim 64).
+//
+//   P = softmax(Q K^T * scale + mask)  -- divide-then-add order and additive -10000 masks exactly as
+//   the reference (pretrain_src/model/vilmodel.py:106-116 self, :332-343 cross);  O = dropout(P) V.
+//
+// The problems are tiny (S = 36 pano views, 53..78 vision tokens, 80 text tokens):
+// one CTA owns one (batch, head) pair, stages Q/K/V in shared memory once, and each warp runs 16
+// query rows through tensor-core MMAs (bf16 inputs, fp32 accumulate) with an online softmax computed
+// with warp shuffles; scores / probabilities never touch HBM (the eager path materialises
+// [N,12,S,S] three times).  The backward recomputes P from the saved log-sum-exp.
+// Q/K/V are read in place from the fused QKV projection output through (batch stride, row pitch).
+#include <stdio.h>
+#include "hamt_common.cuh"
+#include "hamt_kernels.h"
+
+namespace hamt {
+
+static constexpr int D = 64;      // head dim
+static constexpr int LDS = 72;    // smem row pitch in bf16 (144 B: 16-byte aligned rows, conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+struct AttnP {
+  const __nv_bfloat16 *q, *k, *v;
+  long long q_bs, kv_bs, ldq, ldkv;
+  const float* mask;
+  __nv_bfloat16* out; long long ldo, o_bs;
+  float* lse;
+  int B, heads, Sq, Sk;
+  float scale;
+  DropCfg drop;
+  // backward only
+  const __nv_bfloat16* dout; long long lddo, do_bs;
+  __nv_bfloat16 *dq, *dk, *dv;
+};
+
+// cooperative copy of `rows` x 64 bf16 (row pitch ld) into smem [rows_pad][LDS], zero-filling the padding rows
+__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows, int rows_pad) {
+  for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (r < rows) w = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c);
+    *reinterpret_cast<uint4*>(dst + r * LDS + c) = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 63) & ~63;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sK = sQ + Sq_pad * LDS;
+  __nv_bfloat16* sV = sK + Sk_pad * LDS;
+  float* sMask = reinterpret_cast<float*>(sV + Sk_pad * LDS);
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  stage_rows(sQ, p.q + b * p.q_bs + h * D, p.ldq, p.Sq, Sq_pad);
+  stage_rows(sK, p.k + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
+  stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
+  for (int j = threadIdx.x; j < Sk_pad; j += blockDim.x)
+    sMask[j] = j < p.Sk ? (p.mask ? p.mask[(long long)b * p.Sk + j] : 0.f) : -INFINITY;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const DropState ds = drop_init(p.drop);
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+
+  for (int qb = warp; qb < Sq_pad / 16; qb += nwarps) {
+    uint32_t aq[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldsm_x4(aq[ks], sQ_a + 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + ks * 16 + 8 * (lane >> 4)));
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    const int row0 = qb * 16 + g;   // rows row0 and row0 + 8
+
+    for (int kb = 0; kb < Sk_pad / 64; ++kb) {
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bk[4];
+          ldsm_x4(bk, sK_a + 2u * ((kb * 64 + np * 16 + (lane & 7) + 8 * (lane >> 4)) * LDS + ks * 16 + 8 * ((lane >> 3) & 1)));
+          mma16816(s[2 * np], aq[ks], bk[0], bk[1]);
+          mma16816(s[2 * np + 1], aq[ks], bk[2], bk[3]);
+        }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb * 64 + nt * 8 + 2 * t + (e & 1);
+          const float v = s[nt][e] * p.scale + sMask[key];   // padded keys carry -inf
+          s[nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float mn = fmaxf(m[r], quad_max(mx[r]));
+        corr[r] = __expf(m[r] - mn);     // m = -inf on the first block -> 0
+        m[r] = mn;
+        l[r] *= corr[r];
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pe = __expf(s[nt][e] - m[e >> 1]);
+          rs[e >> 1] += pe;
+          float pd = pe;
+          if (ds.on) {
+            const int key = kb * 64 + nt * 8 + 2 * t + (e & 1);
+            const int row = row0 + 8 * (e >> 1);
+            pd *= drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + row) * p.Sk + key);
+          }
+          s[nt][e] = pd;
+        }
+      l[0] += quad_sum(rs[0]);
+      l[1] += quad_sum(rs[1]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+      // O += P_drop (16 x 64 keys) * V (64 keys x 64 d)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ap[4];
+        ap[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        ap[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        ap[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        ap[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bv[4];
+          ldsm_x4_t(bv, sV_a + 2u * ((kb * 64 + kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4)));
+          mma16816(o[2 * dp], ap, bv[0], bv[1]);
+          mma16816(o[2 * dp + 1], ap, bv[2], bv[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + 8 * r;
+      if (row < p.Sq) {
+        const float inv = 1.0f / l[r];
+        __nv_bfloat16* op = p.out + b * p.o_bs + (long long)row * p.ldo + h * D;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * t) = pack_bf16(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+        if (t == 0 && p.lse) p.lse[((long long)b * p.heads + h) * p.Sq + row] = m[r] + __logf(l[r]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward.  Phase 1: warp w owns keys [16w,16w+16): dK, dV in registers, dS^T -> smem.
+//            Phase 2: warp w owns 16 queries: dQ = dS K.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnP p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 15) & ~15;
+  const int LDP = Sk_pad + 8;                       // dS row pitch (bf16); (Sk_pad+8)*2 B is a multiple of 16
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sDO = sQ + Sq_pad * LDS;
+  __nv_bfloat16* sK = sDO + Sq_pad * LDS;
+  __nv_bfloat16* sV = sK + Sk_pad * LDS;
+  __nv_bfloat16* sDS = sV + Sk_pad * LDS;           // [Sq_pad][LDP]
+  float* sMask = reinterpret_cast<float*>(sDS + Sq_pad * LDP);
+  float* sLse = sMask + Sk_pad;
+  float* sDelta = sLse + Sq_pad;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  stage_rows(sQ, p.q + b * p.q_bs + h * D, p.ldq, p.Sq, Sq_pad);
+  stage_rows(sDO, p.dout + b * p.do_bs + h * D, p.lddo, p.Sq, Sq_pad);
+  stage_rows(sK, p.k + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
+  stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
+  for (int j = threadIdx.x; j < Sk_pad; j += blockDim.x) sMask[j] = (j < p.Sk && p.mask) ? p.mask[(long long)b * p.Sk + j] : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // delta_i = sum_d dO[i,d] * O[i,d]  (O = saved forward output)
+  for (int i = warp; i < Sq_pad; i += nwarps) {
+    float acc = 0.f;
+    if (i < p.Sq) {
+      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.dout + b * p.do_bs + (long long)i * p.lddo + h * D + lane * 2));
+      const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.out + b * p.o_bs + (long long)i * p.ldo + h * D + lane * 2));
+      acc = a.x * o.x + a.y * o.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sDelta[i] = acc;
+      sLse[i] = i < p.Sq ? p.lse[((long long)b * p.heads + h) * p.Sq + i] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const DropState ds = drop_init(p.drop);
+  const uint32_t sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDS_a = smem_u32(sDS);
+
+  for (int kw = warp; kw < Sk_pad / 16; kw += nwarps) {
+    uint32_t ak[4][4], av[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t off = 2u * ((kw * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + ks * 16 + 8 * (lane >> 4));
+      ldsm_x4(ak[ks], sK_a + off);
+      ldsm_x4(av[ks], sV_a + off);
+    }
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    const int key0 = kw * 16 + g;   // keys key0, key0 + 8
+    for (int qb = 0; qb < Sq_pad / 16; ++qb) {
+      float st[2][4], dpt[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t bq[4], bd[4];
+        const uint32_t off = 2u * ((qb * 16 + (lane & 7) + 8 * (lane >> 4)) * LDS + ks * 16 + 8 * ((lane >> 3) & 1));
+        ldsm_x4(bq, sQ_a + off);
+        ldsm_x4(bd, sDO_a + off);
+        mma16816(st[0], ak[ks], bq[0], bq[1]);
+        mma16816(st[1], ak[ks], bq[2], bq[3]);
+        mma16816(dpt[0], av[ks], bd[0], bd[1]);
+        mma16816(dpt[1], av[ks], bd[2], bd[3]);
+      }
+      // element (nt, e): key = key0 + 8*(e>>1), query = qb*16 + nt*8 + 2t + (e&1)
+      float pd[2][4], dsv[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + 8 * (e >> 1);
+          const int qi = qb * 16 + nt * 8 + 2 * t + (e & 1);
+          float pe = 0.f, mult = 1.f;
+          if (key < p.Sk && qi < p.Sq) {
+            pe = __expf(st[nt][e] * p.scale + sMask[key] - sLse[qi]);
+            if (ds.on) mult = drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + qi) * p.Sk + key);
+          }
+          pd[nt][e] = pe * mult;
+          dsv[nt][e] = pe * (dpt[nt][e] * mult - sDelta[qi]) * p.scale;
+          sDS[qi * LDP + key] = __float2bfloat16_rn(dsv[nt][e]);
+        }
+      uint32_t ap[4], as_[4];
+      ap[0] = pack_bf16(pd[0][0], pd[0][1]); ap[1] = pack_bf16(pd[0][2], pd[0][3]);
+      ap[2] = pack_bf16(pd[1][0], pd[1][1]); ap[3] = pack_bf16(pd[1][2], pd[1][3]);
+      as_[0] = pack_bf16(dsv[0][0], dsv[0][1]); as_[1] = pack_bf16(dsv[0][2], dsv[0][3]);
+      as_[2] = pack_bf16(dsv[1][0], dsv[1][1]); as_[3] = pack_bf16(dsv[1][2], dsv[1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bdo[4], bqq[4];
+        const uint32_t off = 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4));
+        ldsm_x4_t(bdo, sDO_a + off);
+        ldsm_x4_t(bqq, sQ_a + off);
+        mma16816(dv[2 * dp], ap, bdo[0], bdo[1]);
+        mma16816(dv[2 * dp + 1], ap, bdo[2], bdo[3]);
+        mma16816(dk[2 * dp], as_, bqq[0], bqq[1]);
+        mma16816(dk[2 * dp + 1], as_, bqq[2], bqq[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = key0 + 8 * r;
+      if (key < p.Sk) {
+        __nv_bfloat16* kp = p.dk + b * p.kv_bs + (long long)key * p.ldkv + h * D;
+        __nv_bfloat16* vp = p.dv + b * p.kv_bs + (long long)key * p.ldkv + h * D;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(kp + nt * 8 + 2 * t) = pack_bf16(dk[nt][2 * r], dk[nt][2 * r + 1]);
+          *reinterpret_cast<uint32_t*>(vp + nt * 8 + 2 * t) = pack_bf16(dv[nt][2 * r], dv[nt][2 * r + 1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: dQ[16 x 64] = dS[16 x Sk] K[Sk x 64]
+  for (int qb = warp; qb < Sq_pad / 16; qb += nwarps) {
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    for (int kk = 0; kk < Sk_pad / 16; ++kk) {
+      uint32_t a[4];
+      ldsm_x4(a, sDS_a + 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDP + kk * 16 + 8 * (lane >> 4)));
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bk[4];
+        ldsm_x4_t(bk, sK_a + 2u * ((kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4)));
+        mma16816(dq[2 * dp], a, bk[0], bk[1]);
+        mma16816(dq[2 * dp + 1], a, bk[2], bk[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = qb * 16 + g + 8 * r;
+      if (row < p.Sq) {
+        __nv_bfloat16* qp = p.dq + b * p.q_bs + (long long)row * p.ldq + h * D;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(qp + nt * 8 + 2 * t) = pack_bf16(dq[nt][2 * r], dq[nt][2 * r + 1]);
+      }
+    }
+  }
+}
+
+static int check_common(const AttnArgs& a) {
+  HAMT_REQUIRE(a.B > 0 && a.heads > 0 && a.Sq > 0 && a.Sk > 0, "attn: empty problem");
+  HAMT_REQUIRE((((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.out) & 15) == 0, "attn: q/k/v/out must be 16-byte aligned");
+  HAMT_REQUIRE(a.ldq % 8 == 0 && a.ldkv % 8 == 0 && a.ldo % 8 == 0 && a.q_bstride % 8 == 0 && a.kv_bstride % 8 == 0 && a.o_bstride % 8 == 0,
+               "attn: pitches / batch strides must be multiples of 8 elements");
+  return 0;
+}
+static AttnP to_params(const AttnArgs& a) {
+  AttnP p{};
+  p.q = (const __nv_bfloat16*)a.q; p.k = (const __nv_bfloat16*)a.k; p.v = (const __nv_bfloat16*)a.v;
+  p.q_bs = a.q_bstride; p.kv_bs = a.kv_bstride; p.ldq = a.ldq; p.ldkv = a.ldkv;
+  p.mask = a.mask; p.out = (__nv_bfloat16*)a.out; p.ldo = a.ldo; p.o_bs = a.o_bstride; p.lse = a.lse;
+  p.B = a.B; p.heads = a.heads; p.Sq = a.Sq; p.Sk = a.Sk; p.scale = a.scale;
+  p.drop = DropCfg{a.drop.seed_ptr, a.drop.site, a.drop.p};
+  return p;
+}
+
+int attn_fwd(const AttnArgs& a, cudaStream_t st) {
+  if (int rc = check_common(a)) return rc;
+  AttnP p = to_params(a);
+  const int Sq_pad = (a.Sq + 15) & ~15, Sk_pad = (a.Sk + 63) & ~63;
+  const size_t smem = (size_t)(Sq_pad + 2 * Sk_pad) * LDS * 2 + Sk_pad * 4;
+  HAMT_REQUIRE(smem <= 227 * 1024, "attn_fwd: sequence too long for the single-CTA kernel");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    smem_set = 227 * 1024;
+  }
+  int nw = Sq_pad / 16;
+  if (nw > 8) nw = 8;
+  attn_fwd_kernel<<<a.B * a.heads, nw * 32, smem, st>>>(p);
+  return check_launch("attn_fwd_kernel");
+}
+
+int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
+  if (int rc = check_common(a.f)) return rc;
+  HAMT_REQUIRE(a.f.lse != nullptr, "attn_bwd: lse required");
+  HAMT_REQUIRE((((uintptr_t)a.dout | (uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 15) == 0, "attn_bwd: grads must be 16-byte aligned");
+  AttnP p = to_params(a.f);
+  p.dout = (const __nv_bfloat16*)a.dout; p.lddo = a.lddo; p.do_bs = a.do_bstride;
+  p.dq = (__nv_bfloat16*)a.dq; p.dk = (__nv_bfloat16*)a.dk; p.dv = (__nv_bfloat16*)a.dv;
+  const int Sq_pad = (a.f.Sq + 15) & ~15, Sk_pad = (a.f.Sk + 15) & ~15;
+  const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (size_t)Sq_pad * (Sk_pad + 8) * 2 + (Sk_pad + 2 * Sq_pad) * 4;
+  HAMT_REQUIRE(smem <= 227 * 1024, "attn_bwd: sequence too long for the single-CTA backward kernel");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    smem_set = 227 * 1024;
+  }
+  int nw = (Sk_pad > Sq_pad ? Sk_pad : Sq_pad) / 16;
+  if (nw > 8) nw = 8;
+  attn_bwd_kernel<<<a.f.B * a.f.heads, nw * 32, smem, st>>>(p);
+  return check_launch("attn_bwd_kernel");
+}
+
+}  // namespace hamt

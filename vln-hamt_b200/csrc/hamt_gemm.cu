@@ -1,0 +1,404 @@
+// tcgen05 / TMEM / TMA GEMM for the HAMT hot path (sm_100a).
+//
+//   D[M,N] = sum_k A(m,k) * B(n,k)        bf16 operands, fp32 accumulation in TMEM
+//
+// replaces the eager nn.Linear forward (addmm), its dgrad (mm) and wgrad (mm) of the reference
+// (pretrain_src/model/vilmodel.py:96-98,139-143,168-171,181-185; op census in SURVEY.md 8a).
+//
+// * Each operand is either K-major (reduction index contiguous: activations in forward, dY in
+//   dgrad) or MN-major (output index contiguous: W in dgrad, dY^T and X in wgrad), selected through
+//   the UMMA instruction-descriptor major bits, so no transposed copy of anything is ever made.
+// * Persistent CTAs (one per SM) walk a static list of work units (m-tile, n-tile, k-split).
+//   Warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer, warps 2..9 =
+//   epilogue (TMEM -> registers -> fused bias / GELU / ReLU / dGELU / fp32-accumulate -> global).
+//   smem ring of kStages {A,B} tiles (128-byte swizzle, written by TMA, read by UMMA descriptors),
+//   two TMEM accumulator stages so the epilogue of unit i overlaps the main loop of unit i+1.
+#include <cuda.h>
+#include <stdio.h>
+#include "hamt_common.cuh"
+#include "hamt_kernels.h"
+
+namespace hamt {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + kEpiWarps * 32;
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  void* out;
+  long long ldo;
+  int out_f32;        // 0: bf16 out, 1: fp32 out
+  int out_mode;       // 0: store, 1: out += acc (plain RMW), 2: atomic add (split-K)
+  const float* bias;  // [N] or null
+  int act;            // 0 none, 1 gelu(erf), 2 relu
+  int aux_mode;       // 0 none, 1 store pre-activation (bf16) to aux, 2 multiply by dgelu(aux), 3 multiply by (aux > 0)
+  __nv_bfloat16* aux;
+  long long ld_aux;
+  float alpha;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_ptr_addr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  const int units = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int tn = u % p.tiles_n;
+        const int tm = (u / p.tiles_n) % p.tiles_m;
+        const int sp = u / (p.tiles_n * p.tiles_m);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+          mbar_expect_tx(full_bar(stage), L::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &tma_a, kb * BK, tm * BM, full_bar(stage));
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tma_a, tm * BM + c * 64, kb * BK, full_bar(stage));
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tma_b, kb * BK, tn * BN, full_bar(stage));
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tma_b, tn * BN + c * 64, kb * BK, full_bar(stage));
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int sp = u / (p.tiles_n * p.tiles_m);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 B further along the swizzled row; SBO = 8 rows * 128 B.
+            // MN-major: 16 k-rows = 2048 B further; LBO = stride between 64-element MN chunks
+            // (one TMA box = BK rows * 128 B), SBO = 8 k-rows * 128 B.
+            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int e = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = e >> 2;               // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    const bool out_vec_ok = p.out_f32 ? ((p.ldo & 3) == 0 && ((uintptr_t)p.out & 15) == 0)
+                                      : ((p.ldo & 7) == 0 && ((uintptr_t)p.out & 15) == 0);
+    const bool aux_vec_ok = p.aux != nullptr && (p.ld_aux & 7) == 0 && ((uintptr_t)p.aux & 15) == 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int tn = u % p.tiles_n;
+      const int tm = (u / p.tiles_n) % p.tiles_m;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = tm * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * kColsPerWarp);
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = tn * BN + half * kColsPerWarp + c * 32;
+        if (col0 >= p.N) continue;  // warp-uniform
+        const bool full_chunk = col0 + 32 <= p.N;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_chunk || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.aux_mode == 1 && row_ok) {
+          __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0;
+          if (full_chunk && aux_vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 w = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                   pack_bf16(v[j + 6], v[j + 7]));
+              *reinterpret_cast<uint4*>(ap + j) = w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) ap[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.aux_mode >= 2 && row_ok) {
+          const __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0;
+          float a[32];
+          if (full_chunk && aux_vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 w = *reinterpret_cast<const uint4*>(ap + j);
+              float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+              a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
+              a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) a[j] = (col0 + j < p.N) ? __bfloat162float(ap[j]) : 0.f;
+          }
+          if (p.aux_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(a[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
+          }
+        }
+        if (row_ok) {
+          if (!p.out_f32) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+            if (full_chunk && out_vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 w = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                     pack_bf16(v[j + 6], v[j + 7]));
+                *reinterpret_cast<uint4*>(op + j) = w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) op[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+            if (p.out_mode == 2) {
+              for (int j = 0; j < 32; ++j)
+                if (full_chunk || col0 + j < p.N) atomicAdd(op + j, v[j]);
+            } else if (full_chunk && out_vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.out_mode == 1) {
+                  float4 o = *reinterpret_cast<float4*>(op + j);
+                  w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w;
+                }
+                *reinterpret_cast<float4*>(op + j) = w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) op[j] = (p.out_mode == 1 ? op[j] : 0.f) + v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// rows x cols bf16 matrix, cols contiguous, pitch `ld` elements; box = box_rows x 64 cols, 128B swizzle
+static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  HAMT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  HAMT_REQUIRE(((uintptr_t)ptr & 15) == 0, "gemm operand base must be 16-byte aligned");
+  HAMT_REQUIRE((ld * 2) % 16 == 0, "gemm operand pitch must be a multiple of 8 elements");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    set_last_error(buf);
+    return -2;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    attr_set = true;
+  }
+  const int units = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = units < num_sms() ? units : num_sms();
+  kern<<<grid, kThreads, L::kTotal, st>>>(ta, tb, p);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
+  HAMT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
+  HAMT_REQUIRE(a.out_mode == 0 || a.out_f32, "gemm: accumulate / split-K output must be fp32");
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  int bn = a.tile_n;
+  if (bn != 128 && bn != 256) {
+    // 256-wide tiles halve the smem operand traffic per MMA; use them when the tile count still fills the machine
+    const long long t256 = (long long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
+    bn = (a.N >= 256 && t256 >= 2LL * num_sms()) ? 256 : 128;
+  }
+  p.tiles_m = (a.M + BM - 1) / BM;
+  p.tiles_n = (a.N + bn - 1) / bn;
+  p.kb_total = (a.K + BK - 1) / BK;
+  int splits = 1;
+  if (a.out_mode == 2) {
+    splits = a.splits;
+    if (splits <= 0) {
+      const int tiles = p.tiles_m * p.tiles_n;
+      splits = 1;
+      while (tiles * splits < num_sms() && p.kb_total / (splits * 2) >= 8) splits *= 2;
+    }
+    if (splits > p.kb_total) splits = p.kb_total;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = a.out; p.ldo = a.ldo; p.out_f32 = a.out_f32;
+  p.out_mode = (a.out_mode == 2 && p.splits == 1) ? 1 : a.out_mode;
+  p.bias = a.bias; p.act = a.act; p.aux_mode = a.aux_mode; p.aux = (__nv_bfloat16*)a.aux; p.ld_aux = a.ld_aux;
+  p.alpha = a.alpha;
+  HAMT_REQUIRE(p.aux_mode == 0 || p.aux != nullptr, "gemm: aux_mode set without aux buffer");
+
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: matrix [rows = M or N, cols = K].  MN-major operand: matrix [rows = K, cols = M or N].
+  rc = a.a_mn ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK) : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM);
+  if (rc) return rc;
+  rc = a.b_mn ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, bn);
+  if (rc) return rc;
+
+#define HAMT_DISPATCH(BN_)                                                         \
+  if (!a.a_mn && !a.b_mn) return launch<BN_, false, false>(ta, tb, p, st);        \
+  if (!a.a_mn && a.b_mn) return launch<BN_, false, true>(ta, tb, p, st);          \
+  if (a.a_mn && a.b_mn) return launch<BN_, true, true>(ta, tb, p, st);            \
+  return launch<BN_, true, false>(ta, tb, p, st);
+  if (bn == 256) { HAMT_DISPATCH(256) }
+  HAMT_DISPATCH(128)
+#undef HAMT_DISPATCH
+}
+
+}  // namespace hamt
