@@ -234,7 +234,7 @@ def text_embeddings(sd: State, prefix: str, txt_ids: Tensor, rg: Regime, dp: Opt
 def _feat_embed(sd: State, prefix: str, img: Tensor, ang: Tensor, rg: Regime) -> Tensor:
     """LN(img_linear(x)) + LN(ang_linear(a)); vilmodel.py:497-498.  The angle projection (K=4) is
     done in fp32 on CUDA cores in the product, so it is not quantised in the bf16 regime."""
-    ti = layer_norm(sd, prefix + "img_layer_norm", linear(sd, prefix + "img_linear", img, rg, quant_out=False))
+    ti = layer_norm(sd, prefix + "img_layer_norm", linear(sd, prefix + "img_linear", img, rg))   # GEMM output is stored bf16
     ta = layer_norm(sd, prefix + "ang_layer_norm", linear(sd, prefix + "ang_linear", ang, FP32))
     return ti + ta
 
@@ -284,6 +284,8 @@ def history_embeddings(sd: State, cfg, prefix: str, img: Optional[Tensor], ang: 
     if pos_ids is not None:
         e = e + sd[prefix + ".position_embeddings.weight"][pos_ids]
         e = rg.q(_hidden_drop(layer_norm(sd, prefix + ".layer_norm", e), dp))
+    else:
+        e = rg.q(e)            # ITM: the pre-position sum is materialised (bf16 on the CUDA path)
     return cls, e
 
 
@@ -415,18 +417,21 @@ def backbone_itm(sd: State, cfg, txt_ids, txt_masks, hist_img, hist_ang, hist_pa
 def mlp_head(sd: State, prefix: str, x: Tensor, rg: Regime, dp: Optional[DropPlan], has_dropout: bool) -> Tensor:
     """Linear -> ReLU -> LN(1e-12) -> [Dropout] -> Linear; pretrain_cmt.py:13-71.  The head output
     (logits) is kept fp32."""
-    h = torch.relu(linear(sd, prefix + ".net.0", x, rg, quant_out=False))
-    h = layer_norm(sd, prefix + ".net.2", h)
+    h = rg.q(torch.relu(linear(sd, prefix + ".net.0", x, rg, quant_out=False)))
+    h = rg.q(layer_norm(sd, prefix + ".net.2", h))
     last = ".net.4" if has_dropout else ".net.3"
     if has_dropout:
-        h = _hidden_drop(h, dp)
-    return linear(sd, prefix + last, rg.q(h), rg, quant_out=False)
+        h = rg.q(_hidden_drop(h, dp))
+    w = sd[prefix + last + ".weight"]
+    if w.shape[0] <= 4:      # narrow output: the CUDA path does warp dot products against the fp32 weights
+        return F.linear(h, w, sd[prefix + last + ".bias"])
+    return linear(sd, prefix + last, h, rg, quant_out=False)
 
 
 def mlm_head(sd: State, prefix: str, x: Tensor, rg: Regime) -> Tensor:
     """BertOnlyMLMHead; vilmodel.py:252-295; decoder tied to word embeddings (pretrain_cmt.py:96-99)."""
     p = prefix + ".predictions"
-    h = gelu_erf(linear(sd, p + ".transform.dense", x, rg, quant_out=False))
+    h = rg.q(gelu_erf(linear(sd, p + ".transform.dense", x, rg, quant_out=False)))
     h = rg.q(layer_norm(sd, p + ".transform.LayerNorm", h))
     w = sd[p + ".decoder.weight"]
     return F.linear(h, rg.q(w)) + sd[p + ".bias"]

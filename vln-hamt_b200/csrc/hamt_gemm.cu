@@ -242,13 +242,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             if (full_chunk && out_vec_ok) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
+                if (p.out_mode == 1) {   // bf16 read-modify-write: gradient accumulation onto a residual-path gradient
+                  const uint4 o = *reinterpret_cast<const uint4*>(op + j);
+                  const float2 f0 = unpack_bf16(o.x), f1 = unpack_bf16(o.y), f2 = unpack_bf16(o.z), f3 = unpack_bf16(o.w);
+                  v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+                  v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+                }
                 uint4 w = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
                                      pack_bf16(v[j + 6], v[j + 7]));
                 *reinterpret_cast<uint4*>(op + j) = w;
               }
             } else {
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) op[j] = __float2bfloat16_rn(v[j]);
+                if (col0 + j < p.N) op[j] = __float2bfloat16_rn(v[j] + (p.out_mode == 1 ? __bfloat162float(op[j]) : 0.f));
             }
           } else {
             float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
@@ -353,7 +359,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   HAMT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
-  HAMT_REQUIRE(a.out_mode == 0 || a.out_f32, "gemm: accumulate / split-K output must be fp32");
+  HAMT_REQUIRE(a.out_mode != 2 || a.out_f32, "gemm: split-K accumulation needs an fp32 output");
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   int bn = a.tile_n;

@@ -1,0 +1,549 @@
+"""Fused layer blocks (hand-derived forward + backward) and their autograd wrappers.
+
+Activations are bf16 2-D tensors ``[tokens, hidden]``.  Parameter gradients are written by the CUDA
+kernels directly into the arena (arena.py) -- the autograd graph only carries activation gradients
+between ~20 coarse nodes per step (one per transformer layer / embedder / head op).
+
+Block structure follows the reference modules:
+  attn_block  = BertAttention   (vilmodel.py:146-157)  = fused-QKV GEMM -> fused attention -> dense -> dropout+residual+LN
+  ffn_block   = BertIntermediate + BertOutput (:159-186) = GEMM(+bias+GELU) -> GEMM -> dropout+residual+LN
+  cross_block = BertXAttention in BOTH directions with its shared weights (:351-383)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .arena import ParamArena
+
+BF16 = torch.bfloat16
+
+
+class Run:
+    """Per-forward context: arena, mode, dropout probabilities and the dropout call-site counter."""
+
+    def __init__(self, arena: ParamArena, training: bool, heads: int, eps: float):
+        self.arena = arena
+        self.training = training
+        self.heads = heads
+        self.eps = eps
+        self.save = torch.is_grad_enabled()
+        self._site = 0
+
+    def drop(self, module_or_p) -> ops.Drop:
+        p = module_or_p if isinstance(module_or_p, float) else float(module_or_p.p)
+        if not self.training or p <= 0.0:
+            return ops.NO_DROP
+        self._site += 1
+        return ops.Drop(self.arena.seed, self._site, p)
+
+
+def _wgrad(A: ParamArena, dy: torch.Tensor, x: torch.Tensor, weight):
+    """weight.grad[N,K] += dy[M,N]^T x[M,K]  (both operands MN-major, fp32 split-K accumulation)."""
+    if weight.requires_grad:
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=A.grad(weight), accumulate=True)
+
+
+def _bgrad(A: ParamArena, dy: torch.Tensor, bias):
+    if bias is not None and bias.requires_grad:
+        ops.colsum(dy, A.grad(bias))
+
+
+# ------------------------------------------------------------------------------------------------
+# attention block (self attention)
+# ------------------------------------------------------------------------------------------------
+def _qkv_params(att):
+    return [att.query.weight, att.key.weight, att.value.weight], [att.query.bias, att.key.bias, att.value.bias]
+
+
+def attn_block_fwd(run: Run, x, B: int, S: int, mask, att, out_mod, y_out=None):
+    A, H = run.arena, x.shape[1]
+    ws, bs = _qkv_params(att)
+    qkv = ops.gemm(x, A.fused_w16(ws), bias=A.fused_param(bs))
+    d_attn = run.drop(att.dropout)
+    ctx, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, S, S, run.heads, mask, d_attn, need_lse=run.save)
+    t = ops.gemm(ctx, A.w16(out_mod.dense.weight), bias=out_mod.dense.bias)
+    d_hid = run.drop(out_mod.dropout)
+    ln = out_mod.LayerNorm
+    y, z, mean, rstd = ops.ln_fwd(t, x, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out)
+    saved = (x, qkv, ctx, lse, z, mean, rstd, d_attn, d_hid, mask, B, S) if run.save else None
+    return y, saved
+
+
+def attn_block_bwd(run: Run, dy, saved, att, out_mod, dx_out=None):
+    x, qkv, ctx, lse, z, mean, rstd, d_attn, d_hid, mask, B, S = saved
+    A, H = run.arena, x.shape[1]
+    ws, bs = _qkv_params(att)
+    ln, dense = out_mod.LayerNorm, out_mod.dense
+    dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid, dres_out=dx_out)
+    _wgrad(A, dt, ctx, dense.weight)
+    dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, S, S, run.heads,
+                 mask, d_attn)
+    if ws[0].requires_grad:
+        ops.gemm(dqkv, x, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
+        ops.colsum(dqkv, A.fused_grad(bs))
+    ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)       # dx (residual path) += dqkv @ Wqkv
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# feed-forward block
+# ------------------------------------------------------------------------------------------------
+def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None):
+    A = run.arena
+    w1, w2 = inter.dense.weight, out_mod.dense.weight
+    if run.save:
+        h = torch.empty((x.shape[0], w1.shape[0]), dtype=BF16, device=x.device)
+        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=h)
+    else:
+        h = None
+        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU)
+    t = ops.gemm(a, A.w16(w2), bias=out_mod.dense.bias)
+    d_hid = run.drop(out_mod.dropout)
+    ln = out_mod.LayerNorm
+    y, z, mean, rstd = ops.ln_fwd(t, x, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out)
+    saved = (x, h, a, z, mean, rstd, d_hid) if run.save else None
+    return y, saved
+
+
+def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
+    x, h, a, z, mean, rstd, d_hid = saved
+    A = run.arena
+    ln = out_mod.LayerNorm
+    w1, w2 = inter.dense.weight, out_mod.dense.weight
+    dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(out_mod.dense.bias), drop=d_hid, dres_out=dx_out)
+    _wgrad(A, dt, a, w2)
+    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h)
+    _wgrad(A, dh, x, w1)
+    _bgrad(A, dh, inter.dense.bias)
+    ops.gemm(dh, A.w16(w1), b_mn=True, out=dx, accumulate=True)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# cross attention, both directions, shared weights (rows [0:ML] = language, [ML:] = vision)
+# ------------------------------------------------------------------------------------------------
+def cross_block_fwd(run: Run, xcat, B: int, L: int, V: int, lang_mask, visn_mask, xatt, lang_ca: bool = True):
+    A, H = run.arena, xcat.shape[1]
+    ML = B * L
+    ws, bs = _qkv_params(xatt.att)
+    qkv = ops.gemm(xcat, A.fused_w16(ws), bias=A.fused_param(bs))
+    ctx = torch.empty_like(xcat)
+    d_att_l, d_att_v = run.drop(xatt.att.dropout), run.drop(xatt.att.dropout)
+    lse_l = None
+    if lang_ca:
+        _, lse_l = ops.attn_fwd(qkv[:ML, :H], qkv[ML:, H:2 * H], qkv[ML:, 2 * H:], B, L, V, run.heads, visn_mask, d_att_l, need_lse=run.save, out=ctx[:ML])
+    _, lse_v = ops.attn_fwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v, need_lse=run.save, out=ctx[ML:])
+    ln, dense = xatt.output.LayerNorm, xatt.output.dense
+    d_hid = run.drop(xatt.output.dropout)
+    if lang_ca:
+        t = ops.gemm(ctx, A.w16(dense.weight), bias=dense.bias)
+        y, z, mean, rstd = ops.ln_fwd(t, xcat, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save)
+    else:
+        # finetune no_lang_ca (vilmodel_cmt.py:379-384): language rows pass through unchanged
+        y = torch.empty_like(xcat)
+        y[:ML].copy_(xcat[:ML])
+        t = ops.gemm(ctx[ML:], A.w16(dense.weight), bias=dense.bias)
+        _, z, mean, rstd = ops.ln_fwd(t, xcat[ML:], ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y[ML:])
+    saved = (xcat, qkv, ctx, lse_l, lse_v, z, mean, rstd, d_att_l, d_att_v, d_hid, lang_mask, visn_mask, B, L, V, lang_ca) if run.save else None
+    return y, saved
+
+
+def cross_block_bwd(run: Run, dy, saved, xatt):
+    xcat, qkv, ctx, lse_l, lse_v, z, mean, rstd, d_att_l, d_att_v, d_hid, lang_mask, visn_mask, B, L, V, lang_ca = saved
+    A, H = run.arena, xcat.shape[1]
+    ML = B * L
+    ws, bs = _qkv_params(xatt.att)
+    ln, dense = xatt.output.LayerNorm, xatt.output.dense
+    if lang_ca:
+        dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid)
+        _wgrad(A, dt, ctx, dense.weight)
+        dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(qkv[:ML, :H], qkv[ML:, H:2 * H], qkv[ML:, 2 * H:], ctx[:ML], lse_l, dctx[:ML], dqkv[:ML, :H], dqkv[ML:, H:2 * H],
+                     dqkv[ML:, 2 * H:], B, L, V, run.heads, visn_mask, d_att_l)
+        ops.attn_bwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], ctx[ML:], lse_v, dctx[ML:], dqkv[ML:, :H], dqkv[:ML, H:2 * H],
+                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v)
+    else:
+        dx = torch.empty_like(xcat)
+        dx[:ML].copy_(dy[:ML])
+        dt, _ = ops.ln_bwd(dy[ML:], z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid, dres_out=dx[ML:])
+        _wgrad(A, dt, ctx[ML:], dense.weight)
+        dctx_v = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
+        dqkv = torch.zeros_like(qkv)
+        ops.attn_bwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], ctx[ML:], lse_v, dctx_v, dqkv[ML:, :H], dqkv[:ML, H:2 * H],
+                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v)
+    if ws[0].requires_grad:
+        ops.gemm(dqkv, xcat, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
+        ops.colsum(dqkv, A.fused_grad(bs))
+    ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd wrappers
+# ------------------------------------------------------------------------------------------------
+def _as_bf16_2d(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    g = g.reshape(like.shape)
+    if g.dtype != BF16:
+        g = g.to(BF16)
+    return g.contiguous()
+
+
+class BertLayerFn(torch.autograd.Function):
+    """BertLayer (vilmodel.py:188-201) on rows x [B*S, H]."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, layer, B: int, S: int, mask):
+        y1, s1 = attn_block_fwd(run, x, B, S, mask, layer.attention.self, layer.attention.output)
+        y2, s2 = ffn_block_fwd(run, y1, layer.intermediate, layer.output)
+        ctx.run, ctx.layer, ctx.s1, ctx.s2 = run, layer, s1, s2
+        return y2
+
+    @staticmethod
+    def backward(ctx, dy):
+        run, layer = ctx.run, ctx.layer
+        dy = _as_bf16_2d(dy, ctx.s2[0])
+        d1 = ffn_block_bwd(run, dy, ctx.s2, layer.intermediate, layer.output)
+        dx = attn_block_bwd(run, d1, ctx.s1, layer.attention.self, layer.attention.output)
+        ctx.s1 = ctx.s2 = None
+        return None, dx, None, None, None, None, None
+
+
+class XLayerFn(torch.autograd.Function):
+    """LXRTXLayer (vilmodel.py:362-412) on the joint buffer xcat = [language rows ; vision rows]."""
+
+    @staticmethod
+    def forward(ctx, anchor, xcat, run: Run, layer, B: int, L: int, V: int, lang_mask, visn_mask, lang_ca: bool):
+        ML = B * L
+        y0, s0 = cross_block_fwd(run, xcat, B, L, V, lang_mask, visn_mask, layer.visual_attention, lang_ca)
+        y1 = torch.empty_like(y0)
+        out = torch.empty_like(y0)
+        if lang_ca:
+            _, sl = attn_block_fwd(run, y0[:ML], B, L, lang_mask, layer.lang_self_att.self, layer.lang_self_att.output, y_out=y1[:ML])
+            _, fl = ffn_block_fwd(run, y1[:ML], layer.lang_inter, layer.lang_output, y_out=out[:ML])
+        else:
+            sl = fl = None
+            out[:ML].copy_(y0[:ML])
+        _, sv = attn_block_fwd(run, y0[ML:], B, V, visn_mask, layer.visn_self_att.self, layer.visn_self_att.output, y_out=y1[ML:])
+        _, fv = ffn_block_fwd(run, y1[ML:], layer.visn_inter, layer.visn_output, y_out=out[ML:])
+        ctx.run, ctx.layer, ctx.saved, ctx.ML, ctx.lang_ca = run, layer, (s0, sl, fl, sv, fv), ML, lang_ca
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        run, layer, ML = ctx.run, ctx.layer, ctx.ML
+        s0, sl, fl, sv, fv = ctx.saved
+        dout = _as_bf16_2d(dout, s0[0])
+        d1 = torch.empty_like(dout)
+        d0 = torch.empty_like(dout)
+        if ctx.lang_ca:
+            ffn_block_bwd(run, dout[:ML], fl, layer.lang_inter, layer.lang_output, dx_out=d1[:ML])
+            attn_block_bwd(run, d1[:ML], sl, layer.lang_self_att.self, layer.lang_self_att.output, dx_out=d0[:ML])
+        else:
+            d0[:ML].copy_(dout[:ML])
+        ffn_block_bwd(run, dout[ML:], fv, layer.visn_inter, layer.visn_output, dx_out=d1[ML:])
+        attn_block_bwd(run, d1[ML:], sv, layer.visn_self_att.self, layer.visn_self_att.output, dx_out=d0[ML:])
+        dx = cross_block_bwd(run, d0, s0, layer.visual_attention)
+        ctx.saved = None
+        return (None, dx) + (None,) * 8
+
+
+class LangSelfFn(torch.autograd.Function):
+    """lang_self_att + lang_inter + lang_output of an x-layer, used by the finetune 'language' mode with
+    no_lang_ca (vilmodel_cmt.py:645-652)."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, layer, B: int, L: int, mask):
+        y1, s1 = attn_block_fwd(run, x, B, L, mask, layer.lang_self_att.self, layer.lang_self_att.output)
+        y2, s2 = ffn_block_fwd(run, y1, layer.lang_inter, layer.lang_output)
+        ctx.run, ctx.layer, ctx.s1, ctx.s2 = run, layer, s1, s2
+        return y2
+
+    @staticmethod
+    def backward(ctx, dy):
+        run, layer = ctx.run, ctx.layer
+        dy = _as_bf16_2d(dy, ctx.s2[0])
+        d1 = ffn_block_bwd(run, dy, ctx.s2, layer.lang_inter, layer.lang_output)
+        dx = attn_block_bwd(run, d1, ctx.s1, layer.lang_self_att.self, layer.lang_self_att.output)
+        return None, dx, None, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) for the heads / feature projections.  x bf16 [M,K]; out bf16 (or fp32 logits)."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, lin, act: int, out_f32: bool, need_dx: bool, w_override=None):
+        A = run.arena
+        weight = lin.weight if w_override is None else w_override
+        bias = getattr(lin, "bias", None)
+        w16 = A.w16(weight)
+        pre = None
+        if act != ops.ACT_NONE and run.save:
+            pre = torch.empty((x.shape[0], weight.shape[0]), dtype=BF16, device=x.device)
+            y = ops.gemm(x, w16, bias=bias, act=act, aux_mode=ops.AUX_STORE_PRE, aux=pre)
+        else:
+            out = None
+            if out_f32 and weight.shape[0] % 4:
+                # fp32 logits with an odd class count (30522): pad the row pitch so the epilogue can use 128-bit stores
+                N = weight.shape[0]
+                out = torch.empty((x.shape[0], (N + 7) // 8 * 8), dtype=torch.float32, device=x.device)[:, :N]
+            y = ops.gemm(x, w16, bias=bias, act=act, out=out, out_dtype=torch.float32 if out_f32 else BF16)
+        ctx.run, ctx.weight, ctx.bias, ctx.x, ctx.pre, ctx.act, ctx.need_dx = run, weight, bias, x, pre, act, need_dx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        run, A = ctx.run, ctx.run.arena
+        weight, bias, x, pre, act = ctx.weight, ctx.bias, ctx.x, ctx.pre, ctx.act
+        if dy.dtype != BF16:
+            dy = dy.to(BF16)
+        if dy.stride(-1) != 1 or (dy.stride(0) * 2) % 16 != 0:
+            # TMA operands need a 16-byte row pitch: pad the class dimension (zeros) once
+            N = dy.shape[1]
+            pad = torch.zeros((dy.shape[0], (N + 7) // 8 * 8), dtype=BF16, device=dy.device)
+            pad[:, :N] = dy
+            dy = pad[:, :N]
+        if act == ops.ACT_GELU:
+            dy = _mul_dact(dy, pre, ops.AUX_MUL_DGELU)
+        elif act == ops.ACT_RELU:
+            dy = _mul_dact(dy, pre, ops.AUX_MUL_DRELU)
+        _wgrad(A, dy, x, weight)
+        _bgrad(A, dy, bias)
+        dx = ops.gemm(dy, A.w16(weight), b_mn=True) if ctx.need_dx else None
+        ctx.x = ctx.pre = None
+        return None, dx, None, None, None, None, None, None
+
+
+def _mul_dact(dy, pre, mode):
+    """dy * act'(pre) as a torch elementwise op on small head tensors (M <= a few thousand rows)."""
+    if mode == ops.AUX_MUL_DRELU:
+        return (dy * (pre > 0)).contiguous()
+    p = pre.float()
+    cdf = 0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
+    pdf = 0.3989422804014327 * torch.exp(-0.5 * p * p)
+    return (dy.float() * (cdf + p * pdf)).to(BF16)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """Plain LayerNorm (+ optional dropout AFTER the norm is handled by the caller) for the heads."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, ln):
+        y, _, mean, rstd = ops.ln_fwd(x, None, ln.weight, ln.bias, run.eps, save_z=True, inplace_z=True)
+        ctx.run, ctx.ln, ctx.saved = run, ln, (x, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, ln = ctx.run.arena, ctx.ln
+        x, mean, rstd = ctx.saved
+        dy = _as_bf16_2d(dy, x)
+        dx, _ = ops.ln_bwd(dy, x, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), None, want_dres=False)
+        return None, dx, None, None
+
+
+class RowdotFn(torch.autograd.Function):
+    """Final Linear(H -> N<=4) of a head, fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, lin):
+        ctx.run, ctx.lin, ctx.x = run, lin, x
+        return ops.rowdot_fwd(x, lin.weight, lin.bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, lin = ctx.run.arena, ctx.lin
+        dx = ops.rowdot_bwd(dy.float().contiguous(), ctx.x, lin.weight, A.grad(lin.weight), A.grad(lin.bias) if lin.bias is not None else None)
+        return None, dx, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """F.cross_entropy(reduction='none') on fp32 logits (-inf entries allowed)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        loss, lse = ops.ce_fwd(logits, labels)
+        ctx.saved = (logits, labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        logits, labels, lse = ctx.saved
+        wide = logits.shape[1] > 4096     # MLM: hand the decoder GEMMs a bf16, TMA-aligned gradient directly
+        d = ops.ce_bwd(logits, labels, lse, gloss.float().contiguous(), bf16_padded=wide)
+        return (d[:, :logits.shape[1]] if wide else d), None
+
+
+class TextEmbedFn(torch.autograd.Function):
+    """BertEmbeddings (vilmodel.py:40-69)."""
+
+    @staticmethod
+    def forward(ctx, anchor, run: Run, emb, ids):
+        d = run.drop(emb.dropout)
+        typ0 = emb.token_type_embeddings.weight[0]
+        out = ops.embed_text_fwd(ids, emb.word_embeddings.weight, emb.position_embeddings.weight, typ0, emb.LayerNorm.weight, emb.LayerNorm.bias,
+                                 run.eps, d)
+        ctx.run, ctx.emb, ctx.ids, ctx.d = run, emb, ids, d
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, emb = ctx.run.arena, ctx.emb
+        dy = dy.to(BF16).contiguous()
+        ops.embed_text_bwd(dy, ctx.ids, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
+                           emb.LayerNorm.weight, A.grad(emb.word_embeddings.weight), A.grad(emb.position_embeddings.weight),
+                           A.grad(emb.token_type_embeddings.weight)[0], A.grad(emb.LayerNorm.weight), A.grad(emb.LayerNorm.bias), ctx.run.eps,
+                           ctx.d)
+        return None, None, None, None
+
+
+class FeatEmbedFn(torch.autograd.Function):
+    """LN(img_linear(x)) + LN(ang_linear(a)) [+ ...] [-> LN -> dropout]; the image linear runs on the tensor cores,
+    everything else is one fused row kernel (csrc/hamt_embed.cu).  ``P`` = dict of parameter handles."""
+
+    @staticmethod
+    def forward(ctx, anchor, extra, run: Run, P: dict, x16, ang, nav_ids, pos_ids, pos_mod: int, drop_mod):
+        A = run.arena
+        lin = P["img_linear"]
+        t = ops.gemm(x16, A.w16(lin.weight), bias=lin.bias)
+        d = run.drop(drop_mod) if drop_mod is not None else ops.NO_DROP
+        kw = dict(add_vec=P.get("add_vec"), nav_table=P["nav_table"].weight if nav_ids is not None else None, nav_ids=nav_ids, extra=extra,
+                  pos_table=P["pos_table"].weight if P.get("pos_table") is not None else None, pos_ids=pos_ids, pos_mod=pos_mod,
+                  g_f=P["ln_f"].weight if P.get("ln_f") is not None else None, b_f=P["ln_f"].bias if P.get("ln_f") is not None else None)
+        base = (P["ang_linear"].weight, P["ang_linear"].bias, P["ln_img"].weight, P["ln_img"].bias, P["ln_ang"].weight, P["ln_ang"].bias)
+        out = ops.embed_feat_fwd(t, ang, *base, eps=run.eps, drop=d, **kw)
+        ctx.run, ctx.P, ctx.saved, ctx.kw, ctx.base, ctx.d, ctx.has_extra = run, P, (x16, t, ang), kw, base, d, extra is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        run, P, A = ctx.run, ctx.P, ctx.run.arena
+        x16, t, ang = ctx.saved
+        dy = _as_bf16_2d(dy, t)
+        lin = P["img_linear"]
+        grads = dict(dw_ang=A.grad(P["ang_linear"].weight), db_ang=A.grad(P["ang_linear"].bias), dg_img=A.grad(P["ln_img"].weight),
+                     db_img=A.grad(P["ln_img"].bias), dg_ang=A.grad(P["ln_ang"].weight), dbe_ang=A.grad(P["ln_ang"].bias),
+                     db_lin=A.grad(lin.bias))
+        if P.get("add_vec_grad") is not None:
+            grads["dadd_vec"] = P["add_vec_grad"](A)
+        if ctx.kw["nav_ids"] is not None:
+            grads["dnav_table"] = A.grad(P["nav_table"].weight)
+        if ctx.kw["pos_table"] is not None:
+            grads["dpos_table"] = A.grad(P["pos_table"].weight)
+        if ctx.kw["g_f"] is not None:
+            grads["dg_f"], grads["db_f"] = A.grad(P["ln_f"].weight), A.grad(P["ln_f"].bias)
+        dt, dextra = ops.embed_feat_bwd(dy, t, ang, *ctx.base, grads, eps=run.eps, drop=ctx.d, want_dextra=ctx.has_extra, **ctx.kw)
+        _wgrad(A, dt, x16, lin.weight)
+        ctx.saved = None
+        return (None, dextra) + (None,) * 8
+
+
+class MeanPoolFn(torch.autograd.Function):
+    """torch.mean over the P views of each panorama (vilmodel.py:563-564); bf16 [N*P,H] -> fp32 [N,H]."""
+
+    @staticmethod
+    def forward(ctx, x, N: int, P: int):
+        ctx.N, ctx.P = N, P
+        return ops.mean_pool_fwd(x, N, P)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.mean_pool_bwd(dy.float().contiguous(), ctx.N, ctx.P), None, None
+
+
+class RowLNFn(torch.autograd.Function):
+    """drop(LN(x + res)) on small fp32->bf16 row sets (history CLS token, ITM re-positioned history steps)."""
+
+    @staticmethod
+    def forward(ctx, anchor, x, run: Run, ln, drop_mod):
+        d = run.drop(drop_mod)
+        # fp32 input carried as a bf16 (hi, lo) pair through the kernel's residual slot: hi + lo is summed in fp32
+        x16 = x.to(BF16).contiguous()
+        lo = (x - x16.float()).to(BF16).contiguous()
+        y, z, mean, rstd = ops.ln_fwd(x16, lo, ln.weight, ln.bias, run.eps, save_z=True, inplace_z=True)
+        # dropout AFTER the norm: applied as ln_fwd(dropout(.)) is wrong here, so do it with the streaming kernel trick:
+        ctx.run, ctx.ln, ctx.saved, ctx.d = run, ln, (z, mean, rstd), d
+        if d.p > 0:
+            mask = _post_drop_mask(y, d)
+            y = (y * mask).contiguous()
+            ctx.mask = mask
+        else:
+            ctx.mask = None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, ln = ctx.run.arena, ctx.ln
+        z, mean, rstd = ctx.saved
+        dy = _as_bf16_2d(dy, z)
+        if ctx.mask is not None:
+            dy = (dy * ctx.mask).contiguous()
+        dx, _ = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), None, want_dres=False)
+        return None, dx.float(), None, None, None
+
+
+def _post_drop_mask(y: torch.Tensor, d: ops.Drop) -> torch.Tensor:
+    """Keep-mask * 1/(1-p) generated by the same device hash as every other dropout site: run the LN kernel on a
+    tensor of ones with gamma=1, beta=0 and read the pre-norm z it saves (z = dropout(1))."""
+    ones = torch.ones_like(y)
+    g = torch.ones(y.shape[1], dtype=torch.float32, device=y.device)
+    b = torch.zeros_like(g)
+    _, z, _, _ = ops.ln_fwd(ones, None, g, b, 1e-12, d, save_z=True, inplace_z=True)
+    return z
+
+
+class MulRowsFn(torch.autograd.Function):
+    """ob_embeds * txt_embeds[:, :1] (pretrain_cmt.py:176)."""
+
+    @staticmethod
+    def forward(ctx, a, v, B: int, S: int):
+        ctx.saved, ctx.B, ctx.S = (a, v), B, S
+        return ops.mul_rows(a.contiguous(), v.contiguous(), B, S)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, v = ctx.saved
+        B, S = ctx.B, ctx.S
+        dy = dy.to(BF16).contiguous()
+        da = ops.mul_rows(dy, v.contiguous(), B, S)
+        dv = (dy.float().view(B, S, -1) * a.float().view(B, S, -1)).sum(1).to(BF16)
+        return da, dv, None, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """Stand-alone dropout (head MLPs: ... LN -> Dropout -> Linear, pretrain_cmt.py:16-20) with the device-hash mask."""
+
+    @staticmethod
+    def forward(ctx, x, d: ops.Drop):
+        mask = _post_drop_mask(x, d)
+        ctx.mask = mask
+        return (x * mask).contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (dy.to(BF16) * ctx.mask).contiguous(), None
+
+
+def dropout(run: Run, x: torch.Tensor, module) -> torch.Tensor:
+    d = run.drop(module)
+    return x if d.p <= 0 else DropoutFn.apply(x, d)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """hidden[mask] (_compute_masked_hidden, pretrain_cmt.py:161-165) with precomputed row indices."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.idx, ctx.rows = idx, x.shape[0]
+        return ops.gather_rows(x.contiguous(), idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.scatter_rows(dy.to(BF16).contiguous(), ctx.idx, ctx.rows), None

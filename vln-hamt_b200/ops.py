@@ -67,24 +67,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if out.shape != (M, N) or out.stride(1) != 1 or out.dtype not in (BF16, F32):
         raise ValueError("gemm: bad output tensor")
     out_f32 = 1 if out.dtype == F32 else 0
-    if accumulate and not out_f32:
-        raise ValueError("gemm: accumulate needs an fp32 output")
     if bias is not None and (bias.dtype != F32 or bias.numel() != N):
         raise ValueError("gemm: bias must be fp32 [N]")
     if aux_mode != AUX_NONE:
         _check_bf16_2d(aux, "gemm.aux")
     lib = _lib.load()
     rc = lib.hamt_gemm_bf16(a.data_ptr(), int(a_mn), a.stride(0), b.data_ptr(), int(b_mn), b.stride(0), out.data_ptr(), out.stride(0),
-                            out_f32, 2 if accumulate else 0, M, N, K, _ptr(bias), act, aux_mode, _ptr(aux),
+                            out_f32, (2 if out_f32 else 1) if accumulate else 0, M, N, K, _ptr(bias), act, aux_mode, _ptr(aux),
                             aux.stride(0) if aux is not None else 0, alpha, tile_n, splits, _stream())
     _lib.check(rc, "gemm_bf16")
     return out
 
 
-def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool = True, inplace_z: bool = True):
+def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool = True, inplace_z: bool = True, out=None):
     """y = LN(dropout(x) + res).  Returns (y, z, mean, rstd); z aliases x when inplace_z."""
     M, H = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
     z = (x if inplace_z else torch.empty_like(x)) if save_z else None
     mean = torch.empty(M, dtype=F32, device=x.device) if save_z else None
     rstd = torch.empty(M, dtype=F32, device=x.device) if save_z else None
@@ -95,11 +93,12 @@ def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool =
     return y, z, mean, rstd
 
 
-def ln_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, dbias=None, dres_in=None, want_dx: bool = True, want_dres: bool = True, drop: Drop = NO_DROP):
+def ln_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, dbias=None, dres_in=None, want_dx: bool = True, want_dres: bool = True, drop: Drop = NO_DROP,
+           dres_out=None):
     """Returns (dx, dres); column sums are accumulated into dgamma / dbeta / dbias (fp32)."""
     M, H = dy.shape
     dx = torch.empty_like(dy) if want_dx else None
-    dres = torch.empty_like(dy) if want_dres else None
+    dres = (torch.empty_like(dy) if dres_out is None else dres_out) if want_dres else None
     sp, site, p = drop.args
     rc = _lib.load().hamt_ln_bwd(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _ptr(dres_in), _ptr(dx), _ptr(dres),
                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias), M, H, sp, site, p, _stream())
@@ -107,14 +106,16 @@ def ln_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, dbias=None, dres_in=None, wa
     return dx, dres
 
 
-def attn_fwd(q, k, v, B: int, Sq: int, Sk: int, heads: int, mask: Optional[torch.Tensor], drop: Drop = NO_DROP, need_lse: bool = True):
+def attn_fwd(q, k, v, B: int, Sq: int, Sk: int, heads: int, mask: Optional[torch.Tensor], drop: Drop = NO_DROP, need_lse: bool = True, out=None):
     """q: view [B*Sq, heads*64] (row pitch = stride(0)), k/v: views [B*Sk, heads*64].  Returns (ctx [B*Sq, heads*64], lse)."""
     Hd = heads * 64
-    out = torch.empty((B * Sq, Hd), dtype=BF16, device=q.device)
+    if out is None:
+        out = torch.empty((B * Sq, Hd), dtype=BF16, device=q.device)
     lse = torch.empty((B, heads, Sq), dtype=F32, device=q.device) if need_lse else None
     sp, site, p = drop.args
     rc = _lib.load().hamt_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), Sq * q.stride(0), Sk * k.stride(0), q.stride(0), k.stride(0),
-                                   _ptr(mask), out.data_ptr(), Hd, Sq * Hd, _ptr(lse), B, heads, Sq, Sk, 0.125, sp, site, p, _stream())
+                                   _ptr(mask), out.data_ptr(), out.stride(0), Sq * out.stride(0), _ptr(lse), B, heads, Sq, Sk, 0.125, sp, site, p,
+                                   _stream())
     _lib.check(rc, "attn_fwd")
     return out, lse
 
