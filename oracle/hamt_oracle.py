@@ -142,9 +142,29 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, add_mask: Optional[Tensor], 
     scores = torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(d)
     if add_mask is not None:
         scores = scores + add_mask
-    probs = torch.softmax(scores, dim=-1)
-    probs = _attn_drop(probs, dp)
-    ctx = torch.matmul(rg.q(probs), vh)            # CUDA path feeds P to the PV MMA as bf16
+    if not rg.bf16:
+        probs = torch.softmax(scores, dim=-1)
+        probs = _attn_drop(probs, dp)
+        ctx = torch.matmul(probs, vh)
+    else:
+        # Mirror of csrc/hamt_attn.cu: keys are consumed in blocks of 64 with an online softmax; the UNNORMALISED
+        # block probabilities exp(s - running_max) are rounded to bf16 for the P.V tensor-core product, the row sum
+        # uses the unrounded values, and the 1/l normalisation is applied to the fp32 accumulator at the end.
+        drop_mask = dp.next() if (dp is not None and dp.masks is not None) else None
+        m = torch.full(scores.shape[:-1], -float("inf"))
+        l = torch.zeros(scores.shape[:-1])
+        acc = torch.zeros(B, n_heads, Sq, d)
+        for k0 in range(0, Sk, 64):
+            s = scores[..., k0:k0 + 64]
+            m_new = torch.maximum(m, s.max(-1).values)
+            corr = torch.exp(m - m_new)
+            p = torch.exp(s - m_new[..., None])
+            l = l * corr + p.sum(-1)
+            if drop_mask is not None:
+                p = p * drop_mask[..., k0:k0 + 64].to(p.dtype) / (1.0 - dp.p_attn)
+            acc = acc * corr[..., None] + torch.matmul(rg.q(p), vh[:, :, k0:k0 + 64])
+            m = m_new
+        ctx = acc / l[..., None]
     ctx = ctx.permute(0, 2, 1, 3).contiguous().view(B, Sq, H)
     return rg.q(ctx)
 

@@ -1,0 +1,135 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol include/hamt_b200.h declares
+(no compute calls without a GPU), config / synthetic batches / seeded weights are deterministic, the parameter arena lays the
+fused-QKV slices out contiguously, the product refuses to run without a GPU (no CPU fallback), and the data-parallel
+gradient exchange works with world_size 2 over gloo."""
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib
+    lib = _lib.load()
+    assert lib.hamt_abi_version() == 1
+    decl = set(re.findall(r"\b(hamt_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", "hamt_b200.h")).read()))
+    assert len(decl) >= 24
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/hamt_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert _lib.launch_count() == 0
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_graft_entry_build_runs_on_cpu():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_invalid_arguments_are_reported_not_crashing():
+    """Argument validation happens on the host before any launch, so it can be exercised without a GPU."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib
+    lib = _lib.load()
+    assert lib.hamt_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, 0, 0, 0, 0, None, 0, 0, None, 0, 1.0, 0, 0, None) != 0
+    assert "empty" in _lib.last_error()
+    assert lib.hamt_ln_fwd(None, None, None, None, None, None, None, None, 4, 100, 1e-12, None, 0, 0.0, None) != 0
+    assert "hidden size" in _lib.last_error()
+    assert lib.hamt_rowdot_fwd(None, None, None, None, 4, 9, 768, None) != 0
+
+
+def test_config_and_synthetic_batches_are_deterministic():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import synth
+    from hamt_b200.config import HamtConfig
+    cfg = HamtConfig()
+    assert (cfg.hidden_size, cfg.num_l_layers, cfg.num_x_layers, cfg.num_h_pano_layers, cfg.vocab_size) == (768, 9, 4, 2, 30522)
+    assert HamtConfig.rxr().image_feat_size == 512 and HamtConfig.rxr().vocab_size == 250002
+    for task in ("mlm", "sap", "sar", "sprel", "mrc", "itm"):
+        a = synth.make_batch(task, batch_size=3, txt_len=20, hist_len=4, seed=5, ragged=True)
+        b = synth.make_batch(task, batch_size=3, txt_len=20, hist_len=4, seed=5, ragged=True)
+        for k in a:
+            assert (a[k] is None and b[k] is None) or torch.equal(a[k], b[k])
+        assert a["hist_masks"].shape == (3, 5) and a["hist_masks"][:, 0].all()
+    sap = synth.make_batch("sap", batch_size=4)
+    assert sap["ob_img_fts"].shape == (4, 37, 768) and (sap["ob_img_fts"][:, -1] == 0).all() and (sap["ob_nav_types"][:, -1] == 2).all()
+    assert (sap["ob_nav_types"].gather(1, sap["ob_action_viewindex"][:, None]) != 0).all()
+    assert synth.make_batch("sap", hist_len=0, batch_size=2)["hist_img_fts"] is None
+
+
+def test_arena_layout_and_no_cpu_fallback():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    cfg = HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1)
+    model = MultiStepNavCMTPreTraining(cfg)
+    sd = synth.seeded_state_dict(model, seed=1)
+    model.load_state_dict(sd)
+    arena = model.arena()
+    arena.build()
+    for k, v in model.state_dict().items():                      # values survive re-homing, keys unchanged
+        assert torch.equal(v, sd[k]), k
+    att = model.bert.encoder.layer[0].attention.self
+    fused = arena.fused_param([att.query.weight, att.key.weight, att.value.weight])
+    assert fused.shape == (2304, 768) and torch.equal(fused[768:1536], att.key.weight)
+    fb = arena.fused_param([att.query.bias, att.key.bias, att.value.bias])
+    assert fb.shape == (2304,) and torch.equal(fb[1536:], att.value.bias)
+    assert model.mlm_head.predictions.decoder.weight is model.bert.embeddings.word_embeddings.weight     # tied (pretrain_cmt.py:96-99)
+    g = arena.grad(att.query.weight)
+    assert att.query.weight.grad is g and g.data_ptr() == arena.flat_grad.data_ptr() + 4 * arena.offsets[id(att.query.weight)]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(synth.make_batch("sap", batch_size=2, txt_len=8, hist_len=2), "sap")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, overlap):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import dp
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = MultiStepNavCMTPreTraining(HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1, vocab_size=512))
+    arena = model.arena()
+    arena.build()
+    layer = model.bert.encoder.layer[0]
+    touched = list(layer.parameters()) + [model.next_action.net[0].weight]
+    for i, p in enumerate(touched):                     # fake "backward": rank-dependent gradients written into the arena views
+        arena.grad(p).fill_(float(rank + 1) * (i + 1))
+    untouched = model.itm_head.net[0].weight
+    if overlap:
+        ov = dp.LayerOverlap(arena)
+        ov.layer_done(layer)
+        ov.finish()
+    else:
+        n = dp.sync_grads(arena)
+        assert n >= sum(p.numel() for p in touched)
+    mean = sum(range(1, world + 1)) / world
+    for i, p in enumerate(touched):
+        assert torch.allclose(p.grad, torch.full_like(p.grad, mean * (i + 1))), (rank, i)
+    assert untouched.grad is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_data_parallel_grad_exchange_gloo_world2(overlap):
+    mp.spawn(_dp_worker, args=(2, _free_port(), overlap), nprocs=2, join=True)

@@ -65,8 +65,6 @@ class ParamArena:
     def build(self):
         params = self._ordered_params()
         dev = params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("hamt_b200: the compute path needs the model on a CUDA device (no CPU fallback)")
         total, offsets = 0, {}
         for p in params:
             if p.dtype != torch.float32:
@@ -103,6 +101,8 @@ class ParamArena:
     # ---------------------------------------------------------------- per-step protocol
     def step_begin(self, training: bool):
         """Call at the start of every model forward."""
+        if next(self.module.parameters()).device.type != "cuda":
+            raise RuntimeError("hamt_b200: the compute path needs the model on a CUDA device (no CPU fallback)")
         self.ensure()
         # bf16 shadow refresh: ONE cast launch for every GEMM operand.  Training: every step (weights move every
         # optimizer step; in-place updates through `.data` bump no version counter, so this is unconditional --

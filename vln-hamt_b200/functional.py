@@ -31,6 +31,18 @@ class Run:
         self.eps = eps
         self.save = torch.is_grad_enabled()
         self._site = 0
+        self.uses = {}
+
+    def used(self, layer):
+        self.uses[id(layer)] = self.uses.get(id(layer), 0) + 1
+
+    def done(self, layer):
+        """Called at the end of a layer's backward; fires the data-parallel hook once its gradients are final."""
+        n = self.uses.get(id(layer), 1) - 1
+        self.uses[id(layer)] = n
+        hook = getattr(self.arena, "layer_hook", None)
+        if n == 0 and hook is not None:
+            hook(layer)
 
     def drop(self, module_or_p) -> ops.Drop:
         p = module_or_p if isinstance(module_or_p, float) else float(module_or_p.p)
@@ -202,6 +214,7 @@ class BertLayerFn(torch.autograd.Function):
         y1, s1 = attn_block_fwd(run, x, B, S, mask, layer.attention.self, layer.attention.output)
         y2, s2 = ffn_block_fwd(run, y1, layer.intermediate, layer.output)
         ctx.run, ctx.layer, ctx.s1, ctx.s2 = run, layer, s1, s2
+        run.used(layer)
         return y2
 
     @staticmethod
@@ -211,6 +224,7 @@ class BertLayerFn(torch.autograd.Function):
         d1 = ffn_block_bwd(run, dy, ctx.s2, layer.intermediate, layer.output)
         dx = attn_block_bwd(run, d1, ctx.s1, layer.attention.self, layer.attention.output)
         ctx.s1 = ctx.s2 = None
+        run.done(layer)
         return None, dx, None, None, None, None, None
 
 
@@ -232,6 +246,7 @@ class XLayerFn(torch.autograd.Function):
         _, sv = attn_block_fwd(run, y0[ML:], B, V, visn_mask, layer.visn_self_att.self, layer.visn_self_att.output, y_out=y1[ML:])
         _, fv = ffn_block_fwd(run, y1[ML:], layer.visn_inter, layer.visn_output, y_out=out[ML:])
         ctx.run, ctx.layer, ctx.saved, ctx.ML, ctx.lang_ca = run, layer, (s0, sl, fl, sv, fv), ML, lang_ca
+        run.used(layer)
         return out
 
     @staticmethod
@@ -250,6 +265,7 @@ class XLayerFn(torch.autograd.Function):
         attn_block_bwd(run, d1[ML:], sv, layer.visn_self_att.self, layer.visn_self_att.output, dx_out=d0[ML:])
         dx = cross_block_bwd(run, d0, s0, layer.visual_attention)
         ctx.saved = None
+        run.done(layer)
         return (None, dx) + (None,) * 8
 
 
