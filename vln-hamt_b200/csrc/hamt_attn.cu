@@ -63,7 +63,7 @@ __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat
   }
 }
 
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
+__global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 63) & ~63;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
     const int row0 = qb * 16 + g;   // rows row0 and row0 + 8
 
     for (int kb = 0; kb < Sk_pad / 64; ++kb) {
+      const int ng = min(4, (p.Sk - kb * 64 + 15) >> 4);   // 16-key groups of this block that hold real keys (warp-uniform)
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
       for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
+          if (np >= ng) continue;
           uint32_t bk[4];
           ldsm_x4(bk, sK_a + 2u * ((kb * 64 + np * 16 + (lane & 7) + 8 * (lane >> 4)) * LDS + ks * 16 + 8 * ((lane >> 3) & 1)));
           mma16816(s[2 * np], aq[ks], bk[0], bk[1]);
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
       // O += P_drop (16 x 64 keys) * V (64 keys x 64 d)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= ng) continue;          // probabilities of fully padded groups are exactly zero
         uint32_t ap[4];
         ap[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
         ap[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnP p) {
 // backward.  Phase 1: warp w owns keys [16w,16w+16): dK, dV in registers, dS^T -> smem.
 //            Phase 2: warp w owns 16 queries: dQ = dS K.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnP p) {
+__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 15) & ~15;
   const int LDP = Sk_pad + 8;                       // dS row pitch (bf16); (Sk_pad+8)*2 B is a multiple of 16
@@ -346,11 +349,13 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   const int Sq_pad = (a.Sq + 15) & ~15, Sk_pad = (a.Sk + 63) & ~63;
   const size_t smem = (size_t)(Sq_pad + 2 * Sk_pad) * LDS * 2 + Sk_pad * 4;
   HAMT_REQUIRE(smem <= 227 * 1024, "attn_fwd: sequence too long for the single-CTA kernel");
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    // without the carveout hint the driver sized shared memory for ONE resident CTA (ncu: occupancy_limit_shared_mem = 1)
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
-    smem_set = 227 * 1024;
+    attr_set = true;
   }
   int nw = Sq_pad / 16;
   if (nw > 8) nw = 8;
@@ -368,11 +373,12 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   const int Sq_pad = (a.f.Sq + 15) & ~15, Sk_pad = (a.f.Sk + 15) & ~15;
   const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (size_t)Sq_pad * (Sk_pad + 8) * 2 + (Sk_pad + 2 * Sq_pad) * 4;
   HAMT_REQUIRE(smem <= 227 * 1024, "attn_bwd: sequence too long for the single-CTA backward kernel");
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  static bool attr_set = false;
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
-    smem_set = 227 * 1024;
+    attr_set = true;
   }
   int nw = (Sk_pad > Sq_pad ? Sk_pad : Sq_pad) / 16;
   if (nw > 8) nw = 8;

@@ -71,12 +71,18 @@ __device__ __forceinline__ void ln_back(float (&g)[NCH * 8], const float (&xh)[N
 #pragma unroll
   for (int i = 0; i < NCH * 8; ++i) g[i] = rstd * (g[i] - s1 - xh[i] * s2);
 }
+// accumulate into a WARP-PRIVATE shared-memory row (plain 128-bit read-modify-write, no atomics: shared fp32 atomics cost
+// ~2 cycles per lane and made the first version of the backward 10x slower than its HBM time)
 template <int NCH>
-__device__ __forceinline__ void smem_acc(float* sacc, int lane, const float (&v)[NCH * 8]) {
+__device__ __forceinline__ void smem_acc(float* wacc, int lane, const float (&v)[NCH * 8]) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(sacc + c * 256 + lane * 8 + j, v[c * 8 + j]);
+  for (int c = 0; c < NCH; ++c) {
+    float4* q = reinterpret_cast<float4*>(wacc + c * 256 + lane * 8);
+    float4 a = q[0], b = q[1];
+    a.x += v[c * 8 + 0]; a.y += v[c * 8 + 1]; a.z += v[c * 8 + 2]; a.w += v[c * 8 + 3];
+    b.x += v[c * 8 + 4]; b.y += v[c * 8 + 5]; b.z += v[c * 8 + 6]; b.w += v[c * 8 + 7];
+    q[0] = a; q[1] = b;
+  }
 }
 template <int NCH>
 __device__ __forceinline__ void gmem_acc(float* dst, int lane, const float (&v)[NCH * 8]) {
@@ -127,11 +133,12 @@ __global__ void __launch_bounds__(256) embed_text_bwd_kernel(const __nv_bfloat16
                                                              float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta, int M,
                                                              int L, float eps, DropCfg dc) {
   constexpr int H = NCH * 256;
-  extern __shared__ float sacc[];   // [3][H]: dgamma, dbeta, dtype0
+  extern __shared__ float sall[];   // [warps][3][H]: dgamma, dbeta, dtype0 (warp-private rows)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const DropState ds = drop_init(dc);
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < wpb * 3 * H; i += blockDim.x) sall[i] = 0.f;
   __syncthreads();
+  float* sacc = sall + (threadIdx.x >> 5) * 3 * H;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float xh[NCH * 8], d[NCH * 8], tmp[NCH * 8];
     const long long id = ids[row];
@@ -155,9 +162,11 @@ __global__ void __launch_bounds__(256) embed_text_bwd_kernel(const __nv_bfloat16
   }
   __syncthreads();
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(dgamma + i, sacc[i]);
-    atomicAdd(dbeta + i, sacc[H + i]);
-    atomicAdd(dtype0 + i, sacc[2 * H + i]);
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < wpb; ++w) { a += sall[(w * 3 + 0) * H + i]; b += sall[(w * 3 + 1) * H + i]; c += sall[(w * 3 + 2) * H + i]; }
+    atomicAdd(dgamma + i, a);
+    atomicAdd(dbeta + i, b);
+    atomicAdd(dtype0 + i, c);
   }
 }
 
@@ -234,16 +243,21 @@ __global__ void __launch_bounds__(256) embed_feat_fwd_kernel(const EmbP p) {
 }
 
 // shared accumulator rows
-enum { ACC_DS = 0, ACC_G1, ACC_G2, ACC_DU, ACC_DT, ACC_GF, ACC_BF, ACC_W0, ACC_NAV0 = ACC_W0 + kMaxA, ACC_COUNT = ACC_NAV0 + 3 };
+// accumulator rows (compacted at run time): DS, G1, G2, DU, DT, W[0..A), then GF, BF when there is a final LN, then NAV[0..3)
+enum { ACC_DS = 0, ACC_G1, ACC_G2, ACC_DU, ACC_DT, ACC_W0 };
+__host__ __device__ inline int acc_rows(int A, bool has_f, bool has_nav) { return ACC_W0 + A + (has_f ? 2 : 0) + (has_nav ? 3 : 0); }
 
 template <int NCH>
 __global__ void __launch_bounds__(256) embed_feat_bwd_kernel(const EmbP p) {
   constexpr int H = NCH * 256;
-  extern __shared__ float sacc[];   // [ACC_COUNT][H]
+  extern __shared__ float sall[];   // [warps][rows][H], warp-private
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const DropState ds = drop_init(p.drop);
-  for (int i = threadIdx.x; i < ACC_COUNT * H; i += blockDim.x) sacc[i] = 0.f;
+  const int ACC_GF = ACC_W0 + p.A, ACC_BF = ACC_GF + 1, ACC_NAV0 = p.g_f ? ACC_GF + 2 : ACC_GF;
+  const int nrows = acc_rows(p.A, p.g_f != nullptr, p.dnav_table != nullptr);
+  for (int i = threadIdx.x; i < wpb * nrows * H; i += blockDim.x) sall[i] = 0.f;
   __syncthreads();
+  float* sacc = sall + (threadIdx.x >> 5) * nrows * H;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < p.M; row += gridDim.x * wpb) {
     float x1[NCH * 8], x2[NCH * 8], s[NCH * 8], angv[kMaxA], r1, r2;
     embed_row_forward<NCH>(p, row, lane, x1, r1, x2, r2, s, angv);
@@ -304,6 +318,13 @@ __global__ void __launch_bounds__(256) embed_feat_bwd_kernel(const EmbP p) {
     }
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < nrows * H; i += blockDim.x) {   // fold the warp-private rows into warp 0's
+    float a = sall[i];
+    for (int w = 1; w < wpb; ++w) a += sall[w * nrows * H + i];
+    sall[i] = a;
+  }
+  __syncthreads();
+  sacc = sall;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     const float dsum = sacc[ACC_DS * H + i];
     atomicAdd(p.db_img + i, dsum);
@@ -349,14 +370,19 @@ int embed_feat_fwd(const EmbedFeatArgs& a, cudaStream_t st) {
 
 template <int NCH>
 static int launch_feat_bwd(const EmbP& p, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)ACC_COUNT * NCH * 256 * sizeof(float);
+  const int nrows = acc_rows(p.A, p.g_f != nullptr, p.dnav_table != nullptr);
+  const size_t per_warp = (size_t)nrows * NCH * 256 * sizeof(float);
+  int warps = (int)((220 * 1024) / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) { set_last_error("embed_feat_bwd: accumulator rows do not fit in shared memory"); return -1; }
+  const size_t smem = per_warp * warps;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(embed_feat_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(embed_feat_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
     set = true;
   }
-  embed_feat_bwd_kernel<NCH><<<grid, 256, smem, st>>>(p);
+  embed_feat_bwd_kernel<NCH><<<grid, warps * 32, smem, st>>>(p);
   return check_launch("embed_feat_bwd_kernel");
 }
 
@@ -372,7 +398,7 @@ int embed_feat_bwd(const EmbedFeatBwdArgs& a, cudaStream_t st) {
   p.dy = (const __nv_bfloat16*)a.dy; p.dt = (__nv_bfloat16*)a.dt; p.dw_ang = a.dw_ang; p.db_ang = a.db_ang; p.dg_img = a.dg_img;
   p.db_img = a.db_img; p.dg_ang = a.dg_ang; p.dbe_ang = a.dbe_ang; p.dadd_vec = a.dadd_vec; p.dnav_table = a.dnav_table; p.dextra = a.dextra;
   p.dpos_table = a.dpos_table; p.dg_f = a.dg_f; p.db_f = a.db_f; p.db_lin = a.db_lin;
-  const int grid = rows_grid((f.M + 7) / 8, 148);
+  const int grid = rows_grid((f.M + 3) / 4, 148);
   if (f.H == 768) return launch_feat_bwd<3>(p, grid, st);
   if (f.H == 512) return launch_feat_bwd<2>(p, grid, st);
   return launch_feat_bwd<4>(p, grid, st);
@@ -399,7 +425,14 @@ int embed_text_bwd(const void* dy, const long long* ids, const float* word, cons
   if (M <= 0) return 0;
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
   const int grid = rows_grid((M + 3) / 4, 148 * 2);
-  const size_t smem = (size_t)3 * H * sizeof(float);
+  const size_t smem = (size_t)8 * 3 * H * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(embed_text_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(embed_text_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(embed_text_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    set = true;
+  }
   auto DY = (const __nv_bfloat16*)dy;
   if (H == 768) embed_text_bwd_kernel<3><<<grid, 256, smem, st>>>(DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
   else if (H == 512) embed_text_bwd_kernel<2><<<grid, 256, smem, st>>>(DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);

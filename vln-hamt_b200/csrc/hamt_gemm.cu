@@ -10,9 +10,13 @@
 //   the UMMA instruction-descriptor major bits, so no transposed copy of anything is ever made.
 // * Persistent CTAs (one per SM) walk a static list of work units (m-tile, n-tile, k-split).
 //   Warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer, warps 2..9 =
-//   epilogue (TMEM -> registers -> fused bias / GELU / ReLU / dGELU / fp32-accumulate -> global).
-//   smem ring of kStages {A,B} tiles (128-byte swizzle, written by TMA, read by UMMA descriptors),
-//   two TMEM accumulator stages so the epilogue of unit i overlaps the main loop of unit i+1.
+//   epilogue.  smem ring of kStages {A,B} tiles (128-byte swizzle, written by TMA, read through UMMA
+//   descriptors), two TMEM accumulator stages so the epilogue of unit i overlaps the main loop of
+//   unit i+1.
+// * Epilogue: TMEM -> registers (tcgen05.ld 32x32b) -> fused bias / GELU / ReLU / dGELU / alpha ->
+//   XOR-swizzled per-warp shared-memory transpose -> fully coalesced 128-byte-row global stores
+//   (bf16 store, bf16 read-modify-write, fp32 store / RMW, or red.global.add.v4.f32 for split-K).
+//   The bias slice of the tile is staged once per tile in shared memory.
 #include <cuda.h>
 #include <stdio.h>
 #include "hamt_common.cuh"
@@ -23,7 +27,8 @@ namespace hamt {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 64 + kEpiWarps * 32;
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kThreads = 64 + kEpiThreads;
 
 struct GemmParams {
   int M, N, K;
@@ -46,17 +51,30 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kStagingOffset = kStages * kStageBytes;        // 8 warps x 32 rows x 128 B
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 128;
+  static constexpr int kBiasOffset = kStagingOffset + kStagingBytes;  // 2 x BN floats
+  static constexpr int kBarOffset = kBiasOffset + 2 * BN * 4;
+  static constexpr int kTotal = kBarOffset + 256;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// 16-byte chunk `c` of row `r` inside a warp's [32][128 B] staging tile (XOR swizzle -> conflict-free both ways)
+__device__ __forceinline__ uint32_t stage_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t bar_base = smem_base + L::kBarOffset;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -69,6 +87,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) { printf("hamt gemm: dynamic smem base not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kStages; ++s) {
@@ -163,119 +182,191 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int e = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int half = e >> 2;               // which half of the BN columns
+    const int et = threadIdx.x - 64;       // 0..255 within the epilogue group
     constexpr int kColsPerWarp = BN / 2;
+    uint8_t* stg = smem_raw + L::kStagingOffset + e * (32 * 128);
+    float* sbias = reinterpret_cast<float*>(smem_raw + L::kBiasOffset);
     int as = 0;
     uint32_t aphase = 0;
-    const bool out_vec_ok = p.out_f32 ? ((p.ldo & 3) == 0 && ((uintptr_t)p.out & 15) == 0)
-                                      : ((p.ldo & 7) == 0 && ((uintptr_t)p.out & 15) == 0);
+    const int esz = p.out_f32 ? 4 : 2;
+    const bool out_vec_ok = (((uintptr_t)p.out & 15) == 0) && ((p.ldo * esz) % 16 == 0);
     const bool aux_vec_ok = p.aux != nullptr && (p.ld_aux & 7) == 0 && ((uintptr_t)p.aux & 15) == 0;
+    const bool has_bias = p.bias != nullptr;
+    const int r_sub = lane >> 3, c_sub = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 B per instruction
+
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int tn = u % p.tiles_n;
       const int tm = (u / p.tiles_n) % p.tiles_m;
+      if (has_bias) {   // stage this tile's bias slice (double-buffered by accumulator stage)
+        if (et < BN) sbias[as * BN + et] = (tn * BN + et < p.N) ? __ldg(p.bias + tn * BN + et) : 0.f;
+        epi_bar_sync();
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = tm * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = tm * BM + quarter * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * kColsPerWarp);
+      const float* bias_t = sbias + as * BN + half * kColsPerWarp;
+
+      if (!p.out_f32) {
+        // ---------------- bf16 output: groups of 64 columns (one 128-byte row segment) ----------------
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = tn * BN + half * kColsPerWarp + c * 32;
-        if (col0 >= p.N) continue;  // warp-uniform
-        const bool full_chunk = col0 + 32 <= p.N;
-        float v[32];
+        for (int gI = 0; gI < kColsPerWarp / 64; ++gI) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + gI * 64, r0);
+          tmem_ld_32x32(t_row + gI * 64 + 32, r1);
+          tmem_ld_wait();
+          const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
+          if (col0 >= p.N) continue;  // warp-uniform
+          float v[64];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr) {
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]) * p.alpha; v[32 + j] = __uint_as_float(r1[j]) * p.alpha; }
+          if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full_chunk || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-        }
-        if (p.aux_mode == 1 && row_ok) {
-          __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0;
-          if (full_chunk && aux_vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                                   pack_bf16(v[j + 6], v[j + 7]));
-              *reinterpret_cast<uint4*>(ap + j) = w;
+            for (int j = 0; j < 64; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_t + gI * 64 + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) ap[j] = __float2bfloat16_rn(v[j]);
           }
-        }
-        if (p.act == 1) {
+          const int ncols = min(64, p.N - col0);
+          if (p.aux_mode == 1) {
+            // also emit the pre-activation (needed by the dGELU / dReLU backward)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == 2) {
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) =
+                  make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
+                             pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.aux_mode >= 2 && row_ok) {
-          const __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0;
-          float a[32];
-          if (full_chunk && aux_vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w = *reinterpret_cast<const uint4*>(ap + j);
-              float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
-              a[j] = f0.x; a[j + 1] = f0.y; a[j + 2] = f1.x; a[j + 3] = f1.y;
-              a[j + 4] = f2.x; a[j + 5] = f2.y; a[j + 6] = f3.x; a[j + 7] = f3.y;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) a[j] = (col0 + j < p.N) ? __bfloat162float(ap[j]) : 0.f;
-          }
-          if (p.aux_mode == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(a[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
-          }
-        }
-        if (row_ok) {
-          if (!p.out_f32) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-            if (full_chunk && out_vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (p.out_mode == 1) {   // bf16 read-modify-write: gradient accumulation onto a residual-path gradient
-                  const uint4 o = *reinterpret_cast<const uint4*>(op + j);
-                  const float2 f0 = unpack_bf16(o.x), f1 = unpack_bf16(o.y), f2 = unpack_bf16(o.z), f3 = unpack_bf16(o.w);
-                  v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
-                  v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + r_sub, row = row0 + r;
+              if (row < p.M && c_sub * 8 < ncols) {
+                const uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub));
+                __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0 + c_sub * 8;
+                if (aux_vec_ok && c_sub * 8 + 8 <= ncols) *reinterpret_cast<uint4*>(ap) = w;
+                else {
+                  const __nv_bfloat16* hw = reinterpret_cast<const __nv_bfloat16*>(&w);
+                  for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) ap[j] = hw[j];
                 }
-                uint4 w = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                                     pack_bf16(v[j + 6], v[j + 7]));
-                *reinterpret_cast<uint4*>(op + j) = w;
               }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) op[j] = __float2bfloat16_rn(v[j] + (p.out_mode == 1 ? __bfloat162float(op[j]) : 0.f));
             }
-          } else {
-            float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-            if (p.out_mode == 2) {
-              for (int j = 0; j < 32; ++j)
-                if (full_chunk || col0 + j < p.N) atomicAdd(op + j, v[j]);
-            } else if (full_chunk && out_vec_ok) {
+            __syncwarp();
+          } else if (p.aux_mode >= 2) {
+            // gather the aux tile (pre-activation saved by the forward) coalesced, transpose through smem
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.out_mode == 1) {
-                  float4 o = *reinterpret_cast<float4*>(op + j);
-                  w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w;
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + r_sub, row = row0 + r;
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (row < p.M && c_sub * 8 < ncols) {
+                const __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0 + c_sub * 8;
+                if (aux_vec_ok && c_sub * 8 + 8 <= ncols) w = *reinterpret_cast<const uint4*>(ap);
+                else {
+                  __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
+                  for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) hw[j] = ap[j];
                 }
-                *reinterpret_cast<float4*>(op + j) = w;
               }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) op[j] = (p.out_mode == 1 ? op[j] : 0.f) + v[j];
+              *reinterpret_cast<uint4*>(stg + stage_off(r, c_sub)) = w;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(lane, c));
+              const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+              const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[c * 8 + j] = p.aux_mode == 2 ? v[c * 8 + j] * dgelu_erf(a[j]) : (a[j] > 0.f ? v[c * 8 + j] : 0.f);
+            }
+            __syncwarp();
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) =
+                make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
+                           pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_sub, row = row0 + r;
+            if (row < p.M && c_sub * 8 < ncols) {
+              uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub));
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 8;
+              if (out_vec_ok && c_sub * 8 + 8 <= ncols) {
+                if (p.out_mode == 1) {   // gradient accumulation onto a residual-path gradient
+                  const uint4 o = *reinterpret_cast<const uint4*>(op);
+                  const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, os[4] = {o.x, o.y, o.z, o.w};
+                  uint32_t rs[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 a = unpack_bf16(ws[k]), b = unpack_bf16(os[k]);
+                    rs[k] = pack_bf16(a.x + b.x, a.y + b.y);
+                  }
+                  w = make_uint4(rs[0], rs[1], rs[2], rs[3]);
+                }
+                *reinterpret_cast<uint4*>(op) = w;
+              } else {
+                const __nv_bfloat16* hw = reinterpret_cast<const __nv_bfloat16*>(&w);
+                for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j)
+                  op[j] = p.out_mode == 1 ? __float2bfloat16_rn(__bfloat162float(hw[j]) + __bfloat162float(op[j])) : hw[j];
+              }
             }
           }
+          __syncwarp();
+        }
+      } else {
+        // ---------------- fp32 output: groups of 32 columns (128-byte row segment) ----------------
+#pragma unroll 1
+        for (int gI = 0; gI < kColsPerWarp / 32; ++gI) {
+          uint32_t r0[32];
+          tmem_ld_32x32(t_row + gI * 32, r0);
+          tmem_ld_wait();
+          const int col0 = tn * BN + half * kColsPerWarp + gI * 32;
+          if (col0 >= p.N) continue;
+          const int ncols = min(32, p.N - col0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) * p.alpha;
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bias_t[gI * 32 + j];
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(stg + stage_off(lane, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_sub, row = row0 + r;
+            if (row < p.M && c_sub * 4 < ncols) {
+              float4 w = *reinterpret_cast<const float4*>(stg + stage_off(r, c_sub));
+              float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 4;
+              if (out_vec_ok && c_sub * 4 + 4 <= ncols) {
+                if (p.out_mode == 2) red_add_v4(op, w.x, w.y, w.z, w.w);
+                else {
+                  if (p.out_mode == 1) { const float4 o = *reinterpret_cast<const float4*>(op); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                  *reinterpret_cast<float4*>(op) = w;
+                }
+              } else {
+                const float ws[4] = {w.x, w.y, w.z, w.w};
+                for (int j = 0; j < 4 && c_sub * 4 + j < ncols; ++j) {
+                  if (p.out_mode == 2) atomicAdd(op + j, ws[j]);
+                  else op[j] = (p.out_mode == 1 ? op[j] : 0.f) + ws[j];
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -360,6 +451,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   HAMT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
   HAMT_REQUIRE(a.out_mode != 2 || a.out_f32, "gemm: split-K accumulation needs an fp32 output");
+  HAMT_REQUIRE(a.aux_mode == 0 || !a.out_f32, "gemm: aux epilogues are only implemented for bf16 outputs");
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   int bn = a.tile_n;
