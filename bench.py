@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--tasks", default=None, help="comma list overriding the 6-task schedule (e.g. sap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,7 +152,7 @@ def main():
 
     import torch.distributed as dist
     import hamt_b200  # noqa: F401
-    from hamt_b200 import _lib, dp, ops, synth
+    from hamt_b200 import _lib, dp, graph, ops, synth
     from hamt_b200.config import HamtConfig
     from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
 
@@ -178,16 +179,42 @@ def main():
         b = synth.make_batch(t, batch_size=batch_size_of(t, B), seed=1000 * rank + i, **SHAPE)
         hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
         host_batches.append(hb)
-        dev_batches.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()})
+        db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}
+        if t in ("mlm", "mrc"):      # device-resident leg: the row indices are part of the resident batch
+            db = graph.add_sync_free_extras(t, db)
+            hb = graph.add_sync_free_extras(t, hb)
+            hb = {k: (v.pin_memory() if torch.is_tensor(v) and not v.is_pinned() else v) for k, v in hb.items()}
+            host_batches[-1] = hb
+        if t == "itm":
+            db["_hist_masks_host"] = b["hist_masks"]
+        dev_batches.append(db)
     h2d_bytes = float(np.mean([sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches]))
 
-    def step(i, batch):
-        task = schedule[i % len(schedule)]
-        np.random.seed(i); torch.manual_seed(i)          # ITM negative sampling uses the host RNGs, as in the reference
-        loss = model(batch, task, compute_loss=True)
-        loss.mean().backward()
+    use_graphs = not args.no_graphs
+
+    def exchange():
         if world > 1:
             (overlap.finish() if overlap else dp.sync_grads(arena))
+
+    trainer = graph.GraphedTrainer(model, post_backward=exchange if world > 1 else None) if use_graphs else None
+    graph_launches = {}
+
+    def step(i, batch, eager=False):
+        """One step = one batch of one task: fwd + bwd (+ gradient exchange) + gradient reset.  `batch` may live on the host
+        (pinned) or on the device."""
+        task = schedule[i % len(schedule)]
+        np.random.seed(i); torch.manual_seed(i)          # ITM negative sampling uses the host RNGs, as in the reference
+        if use_graphs and not eager:
+            # masked-row indices (MLM / MRC) and the ITM negative plan are prepared on the host side of the batch
+            b = graph.add_sync_free_extras(task, batch) if ("itm_plan" not in batch and "txt_label_rows" not in batch and "hist_mrc_rows" not in batch) else batch
+            loss = trainer.step(task, b)
+            graph_launches[0] = graph_launches.get(0, 0) + trainer.steps[graph._signature(task, b)].native_launches
+            return loss
+        if not torch.is_tensor(batch["txt_ids"]) or batch["txt_ids"].device.type != "cuda":
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        loss = model(batch, task, compute_loss=True)
+        loss.mean().backward()
+        exchange()
         model.zero_grad(set_to_none=True)
         return loss
 
@@ -206,8 +233,7 @@ def main():
         for i in range(n_steps):
             j = i % len(schedule)
             if from_host:
-                batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batches[j].items()}
-                loss = step(i, batch)
+                loss = step(i, host_batches[j])            # pinned host tensors -> device inside the step
                 val = loss.float().mean().item()           # device -> host read of the step result
                 d2h += 4
                 assert np.isfinite(val)
@@ -221,10 +247,15 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, samples, _lib.launch_count() - launches0, d2h
+        n_launch = _lib.launch_count() - launches0 + graph_launches.pop(0, 0)
+        return ms, samples, n_launch, d2h
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, len(schedule) if use_graphs else 0)):      # every (task, signature) graph is captured in warm-up
         step(i, dev_batches[i % len(schedule)])
+    if use_graphs:
+        for i in range(len(schedule)):
+            step(i, host_batches[i])
+    graph_launches.clear()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, samples, launches, _ = timed(args.steps, from_host=False)
@@ -251,7 +282,7 @@ def main():
     e0.record()
     n_prof = len(schedule)
     for i in range(n_prof):
-        step(i, dev_batches[i % len(schedule)])
+        step(i, dev_batches[i % len(schedule)], eager=True)
     e1.record()
     torch.cuda.synchronize()
     ops.gemm = orig_gemm
@@ -275,7 +306,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "R2R 6-task pretrain (cmt-vitbase-6tasks), txt80/hist15x36/obs37, schedule 5mlm:1sap:1sar:1sprel:2mrc:2itm"
                        if not args.tasks else f"tasks={args.tasks}, txt80/hist15x36/obs37",
-                       "global_batch": B * world, "per_gpu_batch": B, "itm_batch": B // 2, "parallelism": f"dp{world}", "mode": "train (dropout 0.1)",
+                       "global_batch": B * world, "per_gpu_batch": B, "itm_batch": B // 2, "parallelism": f"dp{world}", "mode": "train (dropout 0.1)", "launch": "cuda-graph per (task, batch signature)" if use_graphs else "eager",
                        "l2": "no explicit flush: each step streams ~10 GB of activations + 1.4 GB of weights/grads, >> 126 MB L2",
                        "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else "post-backward all_reduce(AVG)") if world > 1 else "none"},
             "gpu_launches": int(launches),

@@ -1,0 +1,79 @@
+"""CUDA-graph step (graph.py): a replayed captured step must produce the same loss and the same gradients as the eager
+path on the same batch (dropout off), must follow new inputs copied into its static buffers, and must re-seed dropout
+on every replay."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build():
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    model = MultiStepNavCMTPreTraining(HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1))
+    model.load_state_dict(synth.seeded_state_dict(model, seed=3))
+    return model.cuda().train()
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm", "mrc", "itm", "sprel"])
+def test_graph_replay_matches_eager(task):
+    from hamt_b200 import graph, synth
+    model = _build()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    kw = dict(batch_size=4, txt_len=24, hist_len=5)
+    b1 = synth.make_batch(task, seed=1, **kw)
+    b2 = synth.make_batch(task, seed=2, **kw)
+    if task in ("mlm", "mrc"):      # same number of masked rows -> same graph signature
+        key = "txt_labels" if task == "mlm" else "hist_mrc_masks"
+        b2[key] = b1[key].clone()
+        if task == "mlm":
+            b2["txt_ids"] = b1["txt_ids"].clone()
+
+    def eager(b, seed):
+        np.random.seed(seed); torch.manual_seed(seed)
+        model.zero_grad(set_to_none=True)
+        bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+        loss = model(bd, task, compute_loss=True)
+        loss.mean().backward()
+        torch.cuda.synchronize()
+        return loss.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    l1, g1 = eager(b1, 11)
+    l2, g2 = eager(b2, 12)
+    np.random.seed(11); torch.manual_seed(11)
+    trainer = graph.GraphedTrainer(model)
+    e1 = graph.add_sync_free_extras(task, b1)
+    lg1 = trainer.step(task, e1).detach().clone()
+    torch.cuda.synchronize()
+    gg1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert torch.allclose(lg1, l1, atol=2e-3, rtol=1e-3)
+    assert set(gg1) == set(g1)
+    for n in g1:
+        assert (gg1[n] - g1[n]).abs().max().item() <= 2e-2 * g1[n].abs().max().item() + 1e-5, n
+    # new inputs through the same graph
+    np.random.seed(12); torch.manual_seed(12)
+    lg2 = trainer.step(task, graph.add_sync_free_extras(task, b2)).detach().clone()
+    torch.cuda.synchronize()
+    assert len(trainer.steps) == 1
+    assert torch.allclose(lg2, l2, atol=2e-3, rtol=1e-3)
+    gg2 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for n in g2:
+        assert (gg2[n] - g2[n]).abs().max().item() <= 2e-2 * g2[n].abs().max().item() + 1e-5, n
+    # parameters the task does not use keep grad None
+    unused = model.itm_head.net[0].weight if task != "itm" else model.next_action.net[0].weight
+    assert unused.grad is None
+
+
+def test_graph_replay_reseeds_dropout():
+    from hamt_b200 import graph, synth
+    model = _build()
+    b = graph.add_sync_free_extras("sap", synth.make_batch("sap", batch_size=2, txt_len=16, hist_len=3, seed=4))
+    trainer = graph.GraphedTrainer(model)
+    a = trainer.step("sap", b).detach().clone()
+    c = trainer.step("sap", b).detach().clone()
+    assert not torch.equal(a, c)

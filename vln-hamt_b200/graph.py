@@ -1,0 +1,161 @@
+"""CUDA-graph capture of one pretraining step (forward + backward [+ gradient exchange]) per task.
+
+The eager path issues ~470 kernel launches per step from Python (ctypes + autograd), ~17 ms of host work at batch 64
+-- as long as the GPU work itself.  A captured step replays the same launches with one ``cudaGraphLaunch``:
+
+    step = GraphedStep(model, "sap", example_batch)         # captures after 2 warm-up runs
+    loss = step(batch)                                      # copies the batch into the static buffers, replays
+
+What makes the step capturable (host-sync removal):
+  * dropout seeds live in device memory and are advanced by a captured in-place add;
+  * the boolean-mask gathers of MLM / MRC (`hidden[mask]`, pretrain_cmt.py:161-165) use row indices supplied with the
+    batch (computed on the host from the labels the collate function built there anyway) instead of a device `nonzero`;
+    the number of masked rows is part of the graph key;
+  * the ITM negatives (vilmodel.py:676-704) are drawn on the host with the reference's RNG call order and copied into
+    static index buffers before the replay;
+  * weight-gradient accumulation targets (the arena's flat gradient buffer) have fixed addresses.
+All graphs of one model share one memory pool (they never run concurrently).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .vilmodel import itm_negative_plan
+
+_INDEX_KEYS = {"mlm": ("txt_label_rows", "txt_labels", -1), "mrc": ("hist_mrc_rows", "hist_mrc_masks", None)}
+
+
+def add_sync_free_extras(task: str, batch: Dict, device=None) -> Dict:
+    """Augment a (host or device) batch with what the captured step needs: masked-row indices for MLM / MRC and the ITM
+    negative plan.  Uses the global numpy / torch RNGs for ITM exactly like the reference's forward_itm."""
+    b = dict(batch)
+    if task in _INDEX_KEYS:
+        key, src, skip = _INDEX_KEYS[task]
+        m = b[src]
+        mask = (m != skip) if skip is not None else m
+        b[key] = torch.nonzero(mask.reshape(-1), as_tuple=False).squeeze(1)
+    if task == "itm":
+        hm = b.get("_hist_masks_host")           # host copy kept next to a device-resident batch: no device->host sync
+        if hm is None:
+            hm = b["hist_masks"].cpu()
+        neg, shuf = itm_negative_plan(hm.shape[0], hm, b["hist_img_fts"].shape[1], 4)
+        b["itm_plan"] = (neg, shuf)
+    if device is not None:
+        for k, v in list(b.items()):
+            if torch.is_tensor(v):
+                b[k] = v.to(device, non_blocking=True)
+            elif k == "itm_plan":
+                b[k] = (None if v[0] is None else v[0].to(device, non_blocking=True), [t.to(device, non_blocking=True) for t in v[1]])
+    return b
+
+
+def _signature(task, batch):
+    sig = [task]
+    for k in sorted(batch):
+        v = batch[k]
+        if k.startswith("_"):
+            continue
+        if torch.is_tensor(v):
+            sig.append((k, tuple(v.shape), str(v.dtype)))
+        elif k == "itm_plan" and v is not None:
+            sig.append((k, None if v[0] is None else tuple(v[0].shape), len(v[1])))
+        elif v is None:
+            sig.append((k, None))
+    return tuple(sig)
+
+
+class GraphedStep:
+    """One captured `loss = model(batch, task); loss.mean().backward()` for a fixed batch signature."""
+
+    _pools: Dict[int, object] = {}
+
+    def __init__(self, model, task: str, batch: Dict, post_backward=None, warmup: int = 2):
+        self.model, self.task = model, task
+        dev = next(model.parameters()).device
+        self.static = {}
+        for k, v in batch.items():
+            if k.startswith("_"):
+                continue
+            if torch.is_tensor(v):
+                self.static[k] = v.to(dev).clone()
+            elif k == "itm_plan" and v is not None:
+                self.static[k] = (None if v[0] is None else v[0].to(dev).clone(), [t.to(dev).clone() for t in v[1]])
+            else:
+                self.static[k] = v
+        self.signature = _signature(task, batch)
+
+        def body():
+            loss = model(self.static, task, compute_loss=True)
+            loss.mean().backward()
+            if post_backward is not None:
+                post_backward()
+            return loss
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.zero_grad(set_to_none=True)          # the captured step starts by zeroing the flat gradient buffer
+        pool = GraphedStep._pools.get(id(model))
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.loss = body()
+        self.native_launches = _lib.launch_count() - n0
+        if pool is None:
+            GraphedStep._pools[id(model)] = self.graph.pool()
+        # after a replay the gradients of exactly the parameters this task touches are valid
+        self.touched = list(model.arena()._touched)
+        self.touched_ids = {id(p) for p in self.touched}
+
+    def matches(self, task, batch) -> bool:
+        return _signature(task, batch) == self.signature
+
+    def __call__(self, batch: Dict) -> torch.Tensor:
+        for k, v in batch.items():
+            if k.startswith("_"):
+                continue
+            s = self.static.get(k)
+            if torch.is_tensor(v):
+                s.copy_(v, non_blocking=True)
+            elif k == "itm_plan" and v is not None:
+                if v[0] is not None:
+                    s[0].copy_(v[0], non_blocking=True)
+                for dst, src in zip(s[1], v[1]):
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        arena = self.model.arena()
+        # restore the host-side gradient bookkeeping of this task (graphs of other tasks may have run in between)
+        for p in arena._touched:
+            if id(p) not in self.touched_ids:
+                p.grad = None
+        for p in self.touched:
+            if p.grad is None:
+                o = arena.offsets[id(p)]
+                p.grad = arena.flat_grad[o:o + p.numel()].view(p.shape)
+        arena._touched = list(self.touched)
+        arena._sentinel = self.touched[0] if self.touched else None
+        return self.loss
+
+
+class GraphedTrainer:
+    """Cache of captured steps keyed by (task, batch signature); falls back to capture-on-first-use."""
+
+    def __init__(self, model, post_backward=None):
+        self.model, self.post_backward, self.steps = model, post_backward, {}
+
+    def step(self, task: str, batch: Dict) -> torch.Tensor:
+        sig = _signature(task, batch)
+        st = self.steps.get(sig)
+        if st is None:
+            st = GraphedStep(self.model, task, batch, self.post_backward)
+            self.steps[sig] = st
+        return st(batch)

@@ -114,6 +114,9 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
         batch = defaultdict(lambda: None, batch)
         hist = (batch['hist_img_fts'], batch['hist_ang_fts'], batch['hist_pano_img_fts'], batch['hist_pano_ang_fts'], batch['hist_masks'])
         ob = (batch['ob_img_fts'], batch['ob_ang_fts'], batch['ob_nav_types'], batch['ob_masks'])
+        # optional sync-free extras (graph.py): precomputed row indices of the masked tokens / regions and the ITM negative plan
+        self._rows = batch['txt_label_rows'] if task.startswith('mlm') else batch['hist_mrc_rows']
+        self._itm_plan = batch['itm_plan']
         if task.startswith('mlm'):
             return self.forward_mlm(batch['txt_ids'], batch['txt_masks'], *hist, batch['txt_labels'], compute_loss)
         elif task.startswith('sap'):
@@ -130,24 +133,30 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
             raise ValueError('invalid task')
 
     # ------------------------------------------------------------------------------------------
-    def _masked_rows(self, hidden: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-        """hidden[mask] (pretrain_cmt.py:161-165): the row indices come from one nonzero() (host sync, as in the reference)."""
-        H = hidden.shape[-1]
-        idx = torch.nonzero(mask.reshape(-1), as_tuple=False).squeeze(1)
-        return Fn.GatherRowsFn.apply(hidden.reshape(-1, H), idx)
+    def _row_index(self, mask: torch.Tensor) -> torch.Tensor:
+        """Row indices of `mask` (pretrain_cmt.py:161-165).  One nonzero() = one host sync, as in the reference's `hidden[mask]`,
+        unless the caller supplied them with the batch (`txt_label_rows` / `hist_mrc_rows`) -- the CUDA-graph path does."""
+        rows = getattr(self, "_rows", None)
+        if rows is not None:
+            return rows
+        return torch.nonzero(mask.reshape(-1), as_tuple=False).squeeze(1)
+
+    def _masked_rows(self, hidden: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        return Fn.GatherRowsFn.apply(hidden.reshape(-1, hidden.shape[-1]), idx)
 
     def forward_mlm(self, txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts, hist_masks, txt_labels, compute_loss):
         run = self.begin()
         txt_embeds, _, _ = self.bert(txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts, hist_masks,
                                      None, None, None, None, _run=run)
-        masked_output = self._masked_rows(txt_embeds, txt_labels != -1)
+        idx = self._row_index(txt_labels != -1)
+        masked_output = self._masked_rows(txt_embeds, idx)
         pred = self.mlm_head.predictions
         anchor = run.arena.anchor
         h = Fn.LinearFn.apply(anchor, masked_output, run, pred.transform.dense, ops.ACT_GELU, False, True)
         h = Fn.LayerNormFn.apply(anchor, h, run, pred.transform.LayerNorm)
         prediction_scores = Fn.LinearFn.apply(anchor, h, run, _TiedDecoder(pred), ops.ACT_NONE, True, True)
         if compute_loss:
-            return Fn.CrossEntropyFn.apply(prediction_scores, txt_labels[txt_labels != -1])
+            return Fn.CrossEntropyFn.apply(prediction_scores, txt_labels.reshape(-1)[idx])
         return prediction_scores
 
     def forward_sap(self, txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts, hist_masks,
@@ -193,9 +202,10 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
         txt_embeds, hist_embeds, _ = self.bert(txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts, hist_masks,
                                                None, None, None, None, _run=run)
         hist_embeds = hist_embeds[:, 1:]                                                        # remove global embedding
-        masked_output = self._masked_rows(hist_embeds.contiguous(), hist_mrc_masks)
+        idx = self._row_index(hist_mrc_masks)
+        masked_output = self._masked_rows(hist_embeds.contiguous(), idx)
         prediction_soft_labels = self.image_classifier._run(run, masked_output)
-        hist_mrc_targets = hist_img_probs[hist_mrc_masks].float()
+        hist_mrc_targets = hist_img_probs.reshape(-1, hist_img_probs.shape[-1])[idx].float()
         if compute_loss:
             prediction_soft_labels = F.log_softmax(prediction_soft_labels, dim=-1)
             return F.kl_div(prediction_soft_labels, hist_mrc_targets, reduction='none').sum(dim=1)
@@ -205,7 +215,7 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
                     num_neg_trajs, compute_loss):
         run = self.begin()
         fused_embeds = self.bert.forward_itm(txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts, hist_masks,
-                                             num_neg_trajs=num_neg_trajs, _run=run)       # (batch, 1+num_negs, dim)
+                                             num_neg_trajs=num_neg_trajs, _run=run, _plan=getattr(self, "_itm_plan", None))
         B, R, H = fused_embeds.shape
         prediction_scores = self.itm_head._run(run, fused_embeds.reshape(B * R, H)).view(B, R)
         itm_targets = torch.zeros(B, dtype=torch.long, device=fused_embeds.device)

@@ -311,6 +311,30 @@ class HamtPreTrainedModel(nn.Module):
         return Fn.Run(arena, self.training, self.config.num_attention_heads, float(self.config.layer_norm_eps))
 
 
+def itm_negative_plan(batch_size: int, hist_masks: torch.Tensor, hist_max_len: int, num_neg_trajs: int = 4):
+    """Negative-trajectory indices of forward_itm, drawn from the global numpy / torch RNGs in the reference's exact call
+    order (vilmodel.py:676-704): K in-batch negatives per sample via np.random.choice, then K position shuffles via
+    torch.randperm(hist_len) per sample.  Returns (neg_idxs [B,K] or None, [K tensors [B,T]]) on the CPU."""
+    K = num_neg_trajs // 2
+    neg_idxs = None
+    if batch_size > 1:
+        rows = []
+        for i in range(batch_size):
+            rows.append(np.random.choice(np.arange(0, i).tolist() + np.arange(i + 1, batch_size).tolist(), K))
+        neg_idxs = torch.from_numpy(np.stack(rows, 0))
+    else:
+        K = num_neg_trajs
+    hist_lens = (torch.sum(hist_masks, 1) - 1).tolist()
+    shuffled = []
+    for _ in range(K):
+        rows = []
+        for i in range(batch_size):
+            idx = torch.randperm(int(hist_lens[i]))
+            rows.append(torch.cat([idx, torch.arange(int(hist_lens[i]), hist_max_len, dtype=torch.long)], 0))
+        shuffled.append(torch.stack(rows, 0))
+    return neg_idxs, shuffled
+
+
 def _additive_mask(mask: torch.Tensor) -> torch.Tensor:
     """(1 - m) * -10000 as an fp32 row per sample (vilmodel.py:597-599); the kernels add it after the 1/sqrt(d) scale."""
     return ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
@@ -442,7 +466,7 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         return txt, hist_out, ob_out
 
     def forward_itm(self, txt_ids, txt_masks, hist_img_feats, hist_ang_feats, hist_pano_img_feats, hist_pano_ang_feats, hist_masks,
-                    num_neg_trajs=4, _run=None):
+                    num_neg_trajs=4, _run=None, _plan=None):
         """vilmodel.py:640-724.  The negative-trajectory indices are drawn on the host from the global numpy / torch
         RNGs in the reference's exact call order (np.random.choice per sample, then torch.randperm per sample per K)."""
         run = _run or self.begin()
@@ -477,24 +501,15 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         dev = txt_ids.device
         hist = h_layers(torch.cat([cls, with_pos(torch.arange(T, device=dev).expand(B, -1))], 1))
         neg_embeds, neg_masks = [], []
-        K = num_neg_trajs // 2
-        if B > 1:
-            neg_idxs = []
-            for i in range(B):
-                neg_idxs.append(np.random.choice(np.arange(0, i).tolist() + np.arange(i + 1, B).tolist(), K))
-            neg_idxs = torch.from_numpy(np.stack(neg_idxs, 0)).to(dev)
-            for k in range(K):
+        if _plan is None:
+            _plan = itm_negative_plan(B, hist_masks, T, num_neg_trajs)      # host RNG draws in the reference's order (+1 host sync)
+            _plan = (None if _plan[0] is None else _plan[0].to(dev), [t.to(dev) for t in _plan[1]])
+        neg_idxs, shuffled = _plan
+        if neg_idxs is not None:
+            for k in range(neg_idxs.shape[1]):
                 neg_embeds.append(hist[neg_idxs[:, k]])
                 neg_masks.append(hist_mask[neg_idxs[:, k]])
-        else:
-            K = num_neg_trajs
-        hist_lens = (torch.sum(hist_masks, 1) - 1).tolist()
-        for _ in range(K):
-            rows = []
-            for i in range(B):
-                idx = torch.randperm(int(hist_lens[i]))
-                rows.append(torch.cat([idx, torch.arange(int(hist_lens[i]), T, dtype=torch.long)], 0))
-            pos_ids = torch.stack(rows, 0).to(dev)
+        for pos_ids in shuffled:
             neg_embeds.append(h_layers(torch.cat([cls, with_pos(pos_ids)], 1)))
             neg_masks.append(hist_mask)
         visn = torch.cat([hist] + neg_embeds, 0)                                       # [R*B, T+1, H]
