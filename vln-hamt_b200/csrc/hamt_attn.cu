@@ -64,6 +64,7 @@ __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat
 }
 
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 63) & ~63;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
 //            Phase 2: warp w owns 16 queries: dQ = dS K.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 15) & ~15;
   const int LDP = Sk_pad + 8;                       // dS row pitch (bf16); (Sk_pad+8)*2 B is a multiple of 16
@@ -359,7 +361,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   }
   int nw = Sq_pad / 16;
   if (nw > 8) nw = 8;
-  attn_fwd_kernel<<<a.B * a.heads, nw * 32, smem, st>>>(p);
+  launch_pdl(attn_fwd_kernel, a.B * a.heads, nw * 32, smem, st, p);
   return check_launch("attn_fwd_kernel");
 }
 
@@ -382,7 +384,7 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   }
   int nw = (Sk_pad > Sq_pad ? Sk_pad : Sq_pad) / 16;
   if (nw > 8) nw = 8;
-  attn_bwd_kernel<<<a.f.B * a.f.heads, nw * 32, smem, st>>>(p);
+  launch_pdl(attn_bwd_kernel, a.f.B * a.f.heads, nw * 32, smem, st, p);
   return check_launch("attn_bwd_kernel");
 }
 

@@ -22,6 +22,28 @@ int check_launch(const char* what);   // returns 0 or a negative status; records
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_grid_sync(), so the launch latency /
+// CTA scheduling / prologue of kernel i+1 overlaps the tail of kernel i (also inside captured CUDA graphs).
+// griddepcontrol.wait blocks until the preceding grid has completed and flushed its memory, so placing it
+// before the first global-memory access keeps the usual stream-order semantics.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

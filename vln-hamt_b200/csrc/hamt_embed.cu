@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) embed_text_fwd_kernel(const long long* __
                                                              const float* __restrict__ pos, const float* __restrict__ type0,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ out, int M, int L, float eps, DropCfg dc) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const DropState ds = drop_init(dc);
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) embed_text_bwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ type0, const float* __restrict__ gamma,
                                                              float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta, int M,
                                                              int L, float eps, DropCfg dc) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
   extern __shared__ float sall[];   // [warps][3][H]: dgamma, dbeta, dtype0 (warp-private rows)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -184,25 +186,45 @@ struct EmbP {
 
 static constexpr int kMaxA = 8;
 
+// shared-memory loads of a per-column parameter row
+template <int NCH, bool kAdd>
+__device__ __forceinline__ void lds_f32_vec(const float* sp, int lane, float (&v)[NCH * 8]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(sp + c * 256 + lane * 8);
+    const float4 b = *reinterpret_cast<const float4*>(sp + c * 256 + lane * 8 + 4);
+    const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[c * 8 + j] = kAdd ? v[c * 8 + j] + t[j] : t[j];
+  }
+}
+
+// stage W_ang transposed ([A][H], so that a lane's 8 columns are contiguous) + b_ang in shared memory
+template <int NCH>
+__device__ __forceinline__ void stage_wang(const EmbP& p, float* sw) {
+  constexpr int H = NCH * 256;
+  for (int i = threadIdx.x; i < p.A * H; i += blockDim.x) {
+    const int a = i / H, col = i - a * H;
+    sw[i] = __ldg(p.w_ang + (long long)col * p.A + a);
+  }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sw[p.A * H + i] = __ldg(p.b_ang + i);
+}
+
 // forward pieces shared by fwd and bwd: x1 = normalised t, x2 = normalised angle projection, s = sum
 template <int NCH>
-__device__ __forceinline__ void embed_row_forward(const EmbP& p, int row, int lane, float (&x1)[NCH * 8], float& rstd1, float (&x2)[NCH * 8],
-                                                  float& rstd2, float (&s)[NCH * 8], float (&angv)[kMaxA]) {
+__device__ __forceinline__ void embed_row_forward(const EmbP& p, const float* sw, int row, int lane, float (&x1)[NCH * 8], float& rstd1,
+                                                  float (&x2)[NCH * 8], float& rstd2, float (&s)[NCH * 8]) {
   constexpr int H = NCH * 256;
   ld_bf16_row<NCH>(p.t + (long long)row * H, lane, x1);
   rstd1 = normalize<NCH>(x1, p.eps);
+  lds_f32_vec<NCH, false>(sw + p.A * H, lane, x2);                 // b_ang
+  for (int a = 0; a < p.A; ++a) {                                    // K = angle_feat_size (4) projection in fp32 registers
+    const float av = __ldg(p.ang + (long long)row * p.A + a);
+    float w[NCH * 8];
+    lds_f32_vec<NCH, false>(sw + a * H, lane, w);
 #pragma unroll
-  for (int j = 0; j < kMaxA; ++j) angv[j] = j < p.A ? __ldg(p.ang + (long long)row * p.A + j) : 0.f;
-  ld_f32_vec<NCH, false>(p.b_ang, lane, x2);
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float* w = p.w_ang + (long long)(c * 256 + lane * 8 + j) * p.A;
-      float acc = x2[c * 8 + j];
-      for (int a = 0; a < p.A; ++a) acc += angv[a] * __ldg(w + a);
-      x2[c * 8 + j] = acc;
-    }
+    for (int i = 0; i < NCH * 8; ++i) x2[i] += av * w[i];
+  }
   rstd2 = normalize<NCH>(x2, p.eps);
   float g[NCH * 8];
   ld_f32_vec<NCH, false>(p.g_img, lane, g);
@@ -224,12 +246,16 @@ __device__ __forceinline__ void embed_row_forward(const EmbP& p, int row, int la
 
 template <int NCH>
 __global__ void __launch_bounds__(256) embed_feat_fwd_kernel(const EmbP p) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
+  extern __shared__ float sw[];     // [A+1][H]
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const DropState ds = drop_init(p.drop);
+  stage_wang<NCH>(p, sw);
+  __syncthreads();
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < p.M; row += gridDim.x * wpb) {
-    float x1[NCH * 8], x2[NCH * 8], s[NCH * 8], angv[kMaxA], r1, r2;
-    embed_row_forward<NCH>(p, row, lane, x1, r1, x2, r2, s, angv);
+    float x1[NCH * 8], x2[NCH * 8], s[NCH * 8], r1, r2;
+    embed_row_forward<NCH>(p, sw, row, lane, x1, r1, x2, r2, s);
     if (p.g_f) {
       normalize<NCH>(s, p.eps);
       ld_f32_vec<NCH, false>(p.g_f, lane, x1);
@@ -249,18 +275,22 @@ __host__ __device__ inline int acc_rows(int A, bool has_f, bool has_nav) { retur
 
 template <int NCH>
 __global__ void __launch_bounds__(256) embed_feat_bwd_kernel(const EmbP p) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
-  extern __shared__ float sall[];   // [warps][rows][H], warp-private
+  extern __shared__ float smem_f[];   // [A+1][H] staged angle weights, then [warps][rows][H] warp-private accumulators
+  float* sw = smem_f;
+  float* sall = smem_f + (p.A + 1) * H;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const DropState ds = drop_init(p.drop);
+  stage_wang<NCH>(p, sw);
   const int ACC_GF = ACC_W0 + p.A, ACC_BF = ACC_GF + 1, ACC_NAV0 = p.g_f ? ACC_GF + 2 : ACC_GF;
   const int nrows = acc_rows(p.A, p.g_f != nullptr, p.dnav_table != nullptr);
   for (int i = threadIdx.x; i < wpb * nrows * H; i += blockDim.x) sall[i] = 0.f;
   __syncthreads();
   float* sacc = sall + (threadIdx.x >> 5) * nrows * H;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < p.M; row += gridDim.x * wpb) {
-    float x1[NCH * 8], x2[NCH * 8], s[NCH * 8], angv[kMaxA], r1, r2;
-    embed_row_forward<NCH>(p, row, lane, x1, r1, x2, r2, s, angv);
+    float x1[NCH * 8], x2[NCH * 8], s[NCH * 8], r1, r2;
+    embed_row_forward<NCH>(p, sw, row, lane, x1, r1, x2, r2, s);
     float d[NCH * 8], tmp[NCH * 8];
     ld_bf16_row<NCH>(p.dy + (long long)row * H, lane, d);
     apply_drop<NCH>(ds, row, lane, d);
@@ -311,9 +341,10 @@ __global__ void __launch_bounds__(256) embed_feat_bwd_kernel(const EmbP p) {
     ln_back<NCH>(tmp, x2, r2);
     smem_acc<NCH>(sacc + ACC_DU * H, lane, tmp);
     for (int a = 0; a < p.A; ++a) {
+      const float av = __ldg(p.ang + (long long)row * p.A + a);
       float w[NCH * 8];
 #pragma unroll
-      for (int i = 0; i < NCH * 8; ++i) w[i] = tmp[i] * angv[a];
+      for (int i = 0; i < NCH * 8; ++i) w[i] = tmp[i] * av;
       smem_acc<NCH>(sacc + (ACC_W0 + a) * H, lane, w);
     }
   }
@@ -362,9 +393,10 @@ int embed_feat_fwd(const EmbedFeatArgs& a, cudaStream_t st) {
   if (a.M <= 0) return 0;
   EmbP p = to_embp(a);
   const int grid = rows_grid(a.M, 148 * 8);
-  if (a.H == 768) embed_feat_fwd_kernel<3><<<grid, 256, 0, st>>>(p);
-  else if (a.H == 512) embed_feat_fwd_kernel<2><<<grid, 256, 0, st>>>(p);
-  else embed_feat_fwd_kernel<4><<<grid, 256, 0, st>>>(p);
+  const size_t smem = (size_t)(a.A + 1) * a.H * sizeof(float);
+  if (a.H == 768) launch_pdl(embed_feat_fwd_kernel<3>, grid, 256, smem, st, p);
+  else if (a.H == 512) launch_pdl(embed_feat_fwd_kernel<2>, grid, 256, smem, st, p);
+  else launch_pdl(embed_feat_fwd_kernel<4>, grid, 256, smem, st, p);
   return check_launch("embed_feat_fwd_kernel");
 }
 
@@ -372,17 +404,18 @@ template <int NCH>
 static int launch_feat_bwd(const EmbP& p, int grid, cudaStream_t st) {
   const int nrows = acc_rows(p.A, p.g_f != nullptr, p.dnav_table != nullptr);
   const size_t per_warp = (size_t)nrows * NCH * 256 * sizeof(float);
-  int warps = (int)((220 * 1024) / per_warp);
+  const size_t fixed = (size_t)(p.A + 1) * NCH * 256 * sizeof(float);
+  int warps = (int)((224 * 1024 - fixed) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) { set_last_error("embed_feat_bwd: accumulator rows do not fit in shared memory"); return -1; }
-  const size_t smem = per_warp * warps;
+  const size_t smem = fixed + per_warp * warps;
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(embed_feat_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
     set = true;
   }
-  embed_feat_bwd_kernel<NCH><<<grid, warps * 32, smem, st>>>(p);
+  launch_pdl(embed_feat_bwd_kernel<NCH>, grid, warps * 32, smem, st, p);
   return check_launch("embed_feat_bwd_kernel");
 }
 
@@ -412,9 +445,9 @@ int embed_text_fwd(const long long* ids, const float* word, const float* pos, co
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
   const int grid = rows_grid(M, 148 * 8);
   auto O = (__nv_bfloat16*)out;
-  if (H == 768) embed_text_fwd_kernel<3><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
-  else if (H == 512) embed_text_fwd_kernel<2><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
-  else embed_text_fwd_kernel<4><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
+  if (H == 768) launch_pdl(embed_text_fwd_kernel<3>, grid, 256, 0, st, ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
+  else if (H == 512) launch_pdl(embed_text_fwd_kernel<2>, grid, 256, 0, st, ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
+  else launch_pdl(embed_text_fwd_kernel<4>, grid, 256, 0, st, ids, word, pos, type0, gamma, beta, O, M, L, eps, dc);
   return check_launch("embed_text_fwd_kernel");
 }
 
@@ -434,9 +467,9 @@ int embed_text_bwd(const void* dy, const long long* ids, const float* word, cons
     set = true;
   }
   auto DY = (const __nv_bfloat16*)dy;
-  if (H == 768) embed_text_bwd_kernel<3><<<grid, 256, smem, st>>>(DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
-  else if (H == 512) embed_text_bwd_kernel<2><<<grid, 256, smem, st>>>(DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
-  else embed_text_bwd_kernel<4><<<grid, 256, smem, st>>>(DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
+  if (H == 768) launch_pdl(embed_text_bwd_kernel<3>, grid, 256, smem, st, DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
+  else if (H == 512) launch_pdl(embed_text_bwd_kernel<2>, grid, 256, smem, st, DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
+  else launch_pdl(embed_text_bwd_kernel<4>, grid, 256, smem, st, DY, ids, word, pos, type0, gamma, dword, dpos, dtype0, dgamma, dbeta, M, L, eps, dc);
   return check_launch("embed_text_bwd_kernel");
 }
 

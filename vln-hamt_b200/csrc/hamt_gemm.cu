@@ -104,6 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_grid_sync();   // everything above overlapped the previous kernel; global memory is touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -444,7 +445,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   }
   const int units = p.tiles_m * p.tiles_n * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
-  kern<<<grid, kThreads, L::kTotal, st>>>(ta, tb, p);
+  launch_pdl(kern, grid, kThreads, L::kTotal, st, ta, tb, p);
   return check_launch("gemm_tcgen05_kernel");
 }
 
@@ -454,25 +455,39 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   HAMT_REQUIRE(a.aux_mode == 0 || !a.out_f32, "gemm: aux epilogues are only implemented for bf16 outputs");
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
-  int bn = a.tile_n;
-  if (bn != 128 && bn != 256) {
-    // 256-wide tiles halve the smem operand traffic per MMA; use them when the tile count still fills the machine
-    const long long t256 = (long long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256);
-    bn = (a.N >= 256 && t256 >= 2LL * num_sms()) ? 256 : 128;
+  p.kb_total = (a.K + BK - 1) / BK;
+  // Tile width / split-K selection by a small cost model (cycles on one SM; constants from the measured per-k-block
+  // MMA time -- 4 x tcgen05.mma 128xBNx16: BN=256 is tensor-bound at 512 cyc, BN=128 is smem-operand-bound at ~330 cyc --
+  // and the measured epilogue cost per tile).  waves * unit_time + exposed tail.
+  int bn = a.tile_n, splits = a.out_mode == 2 ? a.splits : 1;
+  {
+    const int sms = num_sms(), tm = (a.M + BM - 1) / BM;
+    double best = 1e30;
+    int best_bn = 128, best_s = 1;
+    for (int cand = 256; cand >= 128; cand -= 128) {
+      if (a.tile_n == 128 || a.tile_n == 256) { if (cand != a.tile_n) continue; }
+      else if (cand == 256 && a.N < 192) continue;
+      const int tn = (a.N + cand - 1) / cand;
+      const double t_kb = cand == 256 ? 540.0 : 330.0, t_epi = (cand == 256 ? 2400.0 : 1300.0) * (a.out_f32 ? 1.6 : 1.0);
+      const bool forced = a.out_mode == 2 && a.splits > 0;
+      for (int s = forced ? a.splits : 1; s <= (forced ? a.splits : 32); s *= 2) {
+        if (a.out_mode != 2 && s > 1) break;
+        const int kbs = (p.kb_total + s - 1) / s;
+        if (!forced && s > 1 && kbs < 6) break;
+        const int units = tm * tn * ((p.kb_total + kbs - 1) / kbs);
+        const int waves = (units + sms - 1) / sms;
+        const double unit = kbs * t_kb > t_epi ? kbs * t_kb : t_epi;
+        const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0);
+        if (cost < best) { best = cost; best_bn = cand; best_s = s; }
+      }
+    }
+    bn = best_bn;
+    splits = best_s;
   }
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + bn - 1) / bn;
-  p.kb_total = (a.K + BK - 1) / BK;
-  int splits = 1;
-  if (a.out_mode == 2) {
-    splits = a.splits;
-    if (splits <= 0) {
-      const int tiles = p.tiles_m * p.tiles_n;
-      splits = 1;
-      while (tiles * splits < num_sms() && p.kb_total / (splits * 2) >= 8) splits *= 2;
-    }
-    if (splits > p.kb_total) splits = p.kb_total;
-  }
+  if (splits > p.kb_total) splits = p.kb_total;
+  if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.out = a.out; p.ldo = a.ldo; p.out_f32 = a.out_f32;

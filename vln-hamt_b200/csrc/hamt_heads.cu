@@ -16,6 +16,7 @@ static constexpr int kMaxN = 4;
 // y[m,n] = sum_k x[m,k] w[n,k] + b[n]
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ b, float* __restrict__ y, int M, int N, int H) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float acc[kMaxN] = {0.f, 0.f, 0.f, 0.f};
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, float* dw, float* db,
                                                          int M, int N, int H) {
+  pdl_grid_sync();
   extern __shared__ float sdw[];   // [N][H] + [N]
   for (int i = threadIdx.x; i < N * H + N; i += blockDim.x) sdw[i] = 0.f;
   __syncthreads();
@@ -82,6 +84,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
 }
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                                      float* __restrict__ loss, float* __restrict__ lse, int N) {
+  pdl_grid_sync();
   __shared__ float sh[8];
   const long long row = blockIdx.x;
   const float* p = logits + row * ld;
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                                      const float* __restrict__ lse, const float* __restrict__ gloss, float* dl_f32,
                                                      __nv_bfloat16* dl_bf16, long long ld_d, int N, int N_pad) {
+  pdl_grid_sync();
   const long long row = blockIdx.x;
   const float* p = logits + row * ld;
   const float l = lse[row], g = gloss[row];
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
 // out[i,:] = x[idx[i],:]   /   out[idx[i],:] = x[i,:]   (rows of H bf16, H % 8 == 0)
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ idx, __nv_bfloat16* __restrict__ out, int n,
                                    int H, int scatter) {
+  pdl_grid_sync();
   const int per_row = H / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * per_row; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / per_row;
@@ -135,7 +140,7 @@ int hamt_rowdot_fwd(const void* x, const float* w, const float* b, float* y, int
   if (M <= 0) return 0;
   int grid = (M + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  rowdot_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, b, y, M, N, H);
+  launch_pdl(rowdot_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, w, b, y, M, N, H);
   return check_launch("rowdot_fwd_kernel");
 }
 int hamt_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, float* dw, float* db, int M, int N, int H, void* stream) {
@@ -144,13 +149,13 @@ int hamt_rowdot_bwd(const float* dy, const void* x, const float* w, void* dx, fl
   if (M <= 0) return 0;
   int grid = (M + 31) / 32;
   if (grid > 148) grid = 148;
-  rowdot_bwd_kernel<<<grid, 256, (size_t)(N * H + N) * 4, (cudaStream_t)stream>>>(dy, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dw, db, M, N, H);
+  launch_pdl(rowdot_bwd_kernel, grid, 256, (size_t)(N * H + N) * 4, (cudaStream_t)stream, dy, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)dx, dw, db, M, N, H);
   return check_launch("rowdot_bwd_kernel");
 }
 int hamt_ce_fwd(const float* logits, long long ld, const long long* labels, float* loss, float* lse, int M, int N, void* stream) {
   if (M <= 0) return 0;
   HAMT_REQUIRE(N > 0, "ce: empty class dimension");
-  ce_fwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, loss, lse, N);
+  launch_pdl(ce_fwd_kernel, M, 256, 0, (cudaStream_t)stream, logits, ld, labels, loss, lse, N);
   return check_launch("ce_fwd_kernel");
 }
 int hamt_ce_bwd(const float* logits, long long ld, const long long* labels, const float* lse, const float* gloss, float* dl_f32, void* dl_bf16,
@@ -158,7 +163,7 @@ int hamt_ce_bwd(const float* logits, long long ld, const long long* labels, cons
   if (M <= 0) return 0;
   HAMT_REQUIRE((dl_f32 != nullptr) != (dl_bf16 != nullptr), "ce_bwd: exactly one of dl_f32 / dl_bf16");
   const int n_pad = dl_bf16 ? (int)ld_d : N;   // bf16 output is written out to the padded pitch (zeros) for the TMA GEMM
-  ce_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, lse, gloss, dl_f32, (__nv_bfloat16*)dl_bf16, ld_d, N, n_pad);
+  launch_pdl(ce_bwd_kernel, M, 256, 0, (cudaStream_t)stream, logits, ld, labels, lse, gloss, dl_f32, (__nv_bfloat16*)dl_bf16, ld_d, N, n_pad);
   return check_launch("ce_bwd_kernel");
 }
 int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream) {
@@ -166,7 +171,7 @@ int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n,
   HAMT_REQUIRE(H % 8 == 0, "gather_rows: H must be a multiple of 8");
   int grid = (int)(((long long)n * (H / 8) + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H, 0);
+  launch_pdl(gather_rows_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H, 0);
   return check_launch("gather_rows_kernel");
 }
 int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream) {
@@ -174,7 +179,7 @@ int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n
   HAMT_REQUIRE(H % 8 == 0, "scatter_rows: H must be a multiple of 8");
   int grid = (int)(((long long)n * (H / 8) + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H, 1);
+  launch_pdl(gather_rows_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H, 1);
   return check_launch("scatter_rows_kernel");
 }
 

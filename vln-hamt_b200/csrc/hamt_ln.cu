@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      __nv_bfloat16* __restrict__ y, __nv_bfloat16* z_out, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int M, float eps, DropCfg dc) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
                                                      __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                      float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
+  pdl_grid_sync();
   constexpr int H = NCH * 256;
   __shared__ float sacc[3][H];
   const int lane = threadIdx.x & 31;
@@ -188,9 +190,9 @@ int ln_fwd(const void* x, const void* res, const float* gamma, const float* beta
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
   const int grid = grid_for_rows(M, 8, 148 * 8);
   auto X = (const __nv_bfloat16*)x; auto R = (const __nv_bfloat16*)res; auto Y = (__nv_bfloat16*)y; auto Z = (__nv_bfloat16*)z_out;
-  if (H == 768) ln_fwd_kernel<3><<<grid, 256, 0, st>>>(X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
-  else if (H == 512) ln_fwd_kernel<2><<<grid, 256, 0, st>>>(X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
-  else ln_fwd_kernel<4><<<grid, 256, 0, st>>>(X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
+  if (H == 768) launch_pdl(ln_fwd_kernel<3>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
+  else if (H == 512) launch_pdl(ln_fwd_kernel<2>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
+  else launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
   return check_launch("ln_fwd_kernel");
 }
 
@@ -202,9 +204,9 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
   const int grid = grid_for_rows(M, 8 * 4, 148 * 2);
   auto DY = (const __nv_bfloat16*)dy; auto Z = (const __nv_bfloat16*)z; auto DRI = (const __nv_bfloat16*)dres_in;
   auto DX = (__nv_bfloat16*)dx; auto DR = (__nv_bfloat16*)dres;
-  if (H == 768) ln_bwd_kernel<3><<<grid, 256, 0, st>>>(DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else if (H == 512) ln_bwd_kernel<2><<<grid, 256, 0, st>>>(DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else ln_bwd_kernel<4><<<grid, 256, 0, st>>>(DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  else launch_pdl(ln_bwd_kernel<4>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
   return check_launch("ln_bwd_kernel");
 }
 
@@ -212,6 +214,7 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
 // streaming helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_grid_sync();
   const long long n8 = n >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
@@ -227,12 +230,13 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {
   long long blocks = (n / 8 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cast_kernel<<<(int)blocks, 256, 0, st>>>(in, (__nv_bfloat16*)out, n);
+  launch_pdl(cast_kernel, (int)blocks, 256, 0, st, in, (__nv_bfloat16*)out, n);
   return check_launch("cast_kernel");
 }
 
 // out[n] += sum_m x[m,n].  Block = 32 x 8 threads; each block owns 64 columns (2 per thread-x) and a slice of rows.
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* out, int M, int N, int rows_per_block) {
+  pdl_grid_sync();
   __shared__ float sh[8][64];
   const int c0 = blockIdx.x * 64 + threadIdx.x * 2;
   const int r0 = blockIdx.y * rows_per_block;
@@ -264,12 +268,13 @@ int colsum_bf16(const void* x, long long ld, float* out, int M, int N, cudaStrea
   int rpb = (M + gy - 1) / gy;
   if (rpb < 64) rpb = 64;
   gy = (M + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)x, ld, out, M, N, rpb);
+  launch_pdl(colsum_kernel, dim3(gx, gy), dim3(32, 8), 0, st, (const __nv_bfloat16*)x, ld, out, M, N, rpb);
   return check_launch("colsum_kernel");
 }
 
 // mean over the P tokens of each panorama (reference: torch.mean(dim=2), vilmodel.py:563-564 -- no masking)
 __global__ void mean_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int P, int H) {
+  pdl_grid_sync();
   const int n = blockIdx.x;
   for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
     float a0 = 0.f, a1 = 0.f;
@@ -282,6 +287,7 @@ __global__ void mean_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float*
   }
 }
 __global__ void mean_pool_bwd_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int P, int H) {
+  pdl_grid_sync();
   const int n = blockIdx.x;
   const float inv = 1.0f / P;
   for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
@@ -292,17 +298,18 @@ __global__ void mean_pool_bwd_kernel(const float* __restrict__ dy, __nv_bfloat16
 int mean_pool_fwd(const void* x, float* out, int N, int P, int H, cudaStream_t st) {
   if (N <= 0) return 0;
   HAMT_REQUIRE((H & 1) == 0, "mean_pool: H must be even");
-  mean_pool_fwd_kernel<<<N, 128, 0, st>>>((const __nv_bfloat16*)x, out, N, P, H);
+  launch_pdl(mean_pool_fwd_kernel, N, 128, 0, st, (const __nv_bfloat16*)x, out, N, P, H);
   return check_launch("mean_pool_fwd_kernel");
 }
 int mean_pool_bwd(const float* dy, void* dx, int N, int P, int H, cudaStream_t st) {
   if (N <= 0) return 0;
   HAMT_REQUIRE((H & 1) == 0, "mean_pool: H must be even");
-  mean_pool_bwd_kernel<<<N, 128, 0, st>>>(dy, (__nv_bfloat16*)dx, N, P, H);
+  launch_pdl(mean_pool_bwd_kernel, N, 128, 0, st, dy, (__nv_bfloat16*)dx, N, P, H);
   return check_launch("mean_pool_bwd_kernel");
 }
 
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_grid_sync();
   const long long n8 = n >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i];
@@ -324,12 +331,13 @@ int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t 
   long long blocks = (n / 8 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  add_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+  launch_pdl(add_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
   return check_launch("add_kernel");
 }
 
 // out[b,s,:] = a[b,s,:] * v[b,:]   (SAP fusion  ob_embeds * txt_embeds[:, :1], pretrain_cmt.py:176)
 __global__ void mul_rows_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int S, int H) {
+  pdl_grid_sync();
   const long long row = blockIdx.x;
   const int b = (int)(row / S);
   for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
@@ -341,7 +349,7 @@ __global__ void mul_rows_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 int mul_rows_bf16(const void* a, const void* b, void* out, int B, int S, int H, cudaStream_t st) {
   if (B * S <= 0) return 0;
   HAMT_REQUIRE((H & 1) == 0, "mul_rows: H must be even");
-  mul_rows_kernel<<<B * S, 128, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, S, H);
+  launch_pdl(mul_rows_kernel, B * S, 128, 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, S, H);
   return check_launch("mul_rows_kernel");
 }
 
