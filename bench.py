@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--tasks", default=None, help="comma list overriding the 6-task schedule (e.g. sap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--dp-mode", default="graph", choices=["graph", "after", "overlap"],
+                    help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -169,7 +171,7 @@ def main():
     arena = model.arena()
     arena.ensure()
     overlap = None
-    if world > 1 and not args.no_overlap:
+    if world > 1 and args.dp_mode == "overlap" and args.no_graphs:
         overlap = dp.LayerOverlap(arena)
         arena.layer_hook = overlap.layer_done
 
@@ -196,7 +198,8 @@ def main():
         if world > 1:
             (overlap.finish() if overlap else dp.sync_grads(arena))
 
-    trainer = graph.GraphedTrainer(model, post_backward=exchange if world > 1 else None) if use_graphs else None
+    in_graph = world > 1 and args.dp_mode == "graph"
+    trainer = graph.GraphedTrainer(model, post_backward=exchange if in_graph else None) if use_graphs else None
     graph_launches = {}
 
     def step(i, batch, eager=False):
@@ -208,6 +211,8 @@ def main():
             # masked-row indices (MLM / MRC) and the ITM negative plan are prepared on the host side of the batch
             b = graph.add_sync_free_extras(task, batch) if ("itm_plan" not in batch and "txt_label_rows" not in batch and "hist_mrc_rows" not in batch) else batch
             loss = trainer.step(task, b)
+            if world > 1 and not in_graph:
+                exchange()
             graph_launches[0] = graph_launches.get(0, 0) + trainer.steps[graph._signature(task, b)].native_launches
             return loss
         if not torch.is_tensor(batch["txt_ids"]) or batch["txt_ids"].device.type != "cuda":
@@ -315,7 +320,9 @@ def main():
                        if not args.tasks else f"tasks={args.tasks}, txt80/hist15x36/obs37",
                        "global_batch": B * world, "per_gpu_batch": B, "itm_batch": B // 2, "parallelism": f"dp{world}", "mode": "train (dropout 0.1)", "launch": "cuda-graph per (task, batch signature)" if use_graphs else "eager",
                        "l2": "no explicit flush: each step streams ~10 GB of activations + 1.4 GB of weights/grads, >> 126 MB L2",
-                       "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else "post-backward all_reduce(AVG)") if world > 1 else "none"},
+                       "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else
+                                         ("all_reduce(AVG) on the flat fp32 grad slices, " + ("captured at the end of the step graph" if in_graph and use_graphs else "after backward")))
+                       if world > 1 else "none"},
             "gpu_launches": int(launches),
             "model_tflops": round(alg_flops_per_step * args.steps / (ms * 1e-3) / 1e12 * 1.0, 1),
             "clocks": clocks,

@@ -107,7 +107,8 @@ class GraphedStep:
         pool = GraphedStep._pools.get(id(model))
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph, pool=pool):
+        # thread_local: the NCCL watchdog thread (data-parallel runs) polls CUDA events while we capture
+        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode="thread_local"):
             self.loss = body()
         self.native_launches = _lib.launch_count() - n0
         if pool is None:
