@@ -171,7 +171,7 @@ def main():
     arena = model.arena()
     arena.ensure()
     overlap = None
-    if world > 1 and args.dp_mode == "overlap" and args.no_graphs:
+    if world > 1 and args.dp_mode == "overlap":
         overlap = dp.LayerOverlap(arena)
         arena.layer_hook = overlap.layer_done
 
@@ -198,7 +198,7 @@ def main():
         if world > 1:
             (overlap.finish() if overlap else dp.sync_grads(arena))
 
-    in_graph = world > 1 and args.dp_mode == "graph"
+    in_graph = world > 1 and args.dp_mode in ("graph", "overlap")
     trainer = graph.GraphedTrainer(model, post_backward=exchange if in_graph else None) if use_graphs else None
     graph_launches = {}
 
@@ -340,8 +340,14 @@ def main():
                                     "sample": f"oracle port fp32 fwd+bwd, 1 SAP + 1 MLM step at batch {args.ref_batch} ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            if trainer is not None:
+                trainer.steps.clear()          # drop the captured graphs (they hold NCCL work) before the group goes away
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as e:  # pragma: no cover - teardown only
+            print(f"[bench] teardown: {type(e).__name__}: {e}", file=sys.stderr)
 
 
 if __name__ == "__main__":
