@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--tasks", default=None, help="comma list overriding the 6-task schedule (e.g. sap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--dp-mode", default="graph", choices=["graph", "after", "overlap"],
+    ap.add_argument("--dp-mode", default="overlap", choices=["graph", "after", "overlap"],
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     args = ap.parse_args()
