@@ -229,22 +229,56 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(i):
+        """Host -> device copy of step i's batch from pinned memory on a side stream, like the reference's PrefetchLoader
+        (pretrain_src/data/loader.py:90-125): the copy of batch i+1 overlaps the compute of batch i."""
+        j = i % len(schedule)
+        task = schedule[j]
+        np.random.seed(i); torch.manual_seed(i)
+        hb = graph.add_sync_free_extras(task, host_batches[j]) if (use_graphs and task == "itm") else host_batches[j]
+        with torch.cuda.stream(copy_stream):
+            db = {}
+            for k, v in hb.items():
+                if torch.is_tensor(v):
+                    db[k] = v.to(dev, non_blocking=True)
+                elif k == "itm_plan" and v is not None:
+                    db[k] = (None if v[0] is None else v[0].to(dev, non_blocking=True), [t.to(dev, non_blocking=True) for t in v[1]])
+                else:
+                    db[k] = v
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return db, ev
+
     def timed(n_steps, from_host):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = _lib.launch_count()
         e0.record()
         samples, d2h = 0, 0
+        nxt = prefetch(0) if from_host else None
+        prev = None
         for i in range(n_steps):
             j = i % len(schedule)
             if from_host:
-                loss = step(i, host_batches[j])            # pinned host tensors -> device inside the step
-                val = loss.float().mean().item()           # device -> host read of the step result
-                d2h += 4
-                assert np.isfinite(val)
+                (batch, ev), nxt = nxt, (prefetch(i + 1) if i + 1 < n_steps else None)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for v in batch.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(cur)
+                lm = step(i, batch).float().mean()         # tiny reduction enqueued behind the step
+                if prev is not None:                       # device -> host read of the previous step's result while this one runs
+                    assert np.isfinite(prev.item())
+                    d2h += 4
+                prev = lm
             else:
                 step(i, dev_batches[j])
             samples += batch_size_of(schedule[j], B)
+        if prev is not None:
+            assert np.isfinite(prev.item())
+            d2h += 4
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
