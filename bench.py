@@ -231,6 +231,8 @@ def main():
 
     copy_stream = torch.cuda.Stream(device=dev)
 
+    staging = [None] * len(schedule)     # persistent device staging buffers, one set per schedule slot (no allocation in the loop)
+
     def prefetch(i):
         """Host -> device copy of step i's batch from pinned memory on a side stream, like the reference's PrefetchLoader
         (pretrain_src/data/loader.py:90-125): the copy of batch i+1 overlaps the compute of batch i."""
@@ -238,15 +240,27 @@ def main():
         task = schedule[j]
         np.random.seed(i); torch.manual_seed(i)
         hb = graph.add_sync_free_extras(task, host_batches[j]) if (use_graphs and task == "itm") else host_batches[j]
-        with torch.cuda.stream(copy_stream):
-            db = {}
+        if staging[j] is None:
+            st = {}
             for k, v in hb.items():
                 if torch.is_tensor(v):
-                    db[k] = v.to(dev, non_blocking=True)
+                    st[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
                 elif k == "itm_plan" and v is not None:
-                    db[k] = (None if v[0] is None else v[0].to(dev, non_blocking=True), [t.to(dev, non_blocking=True) for t in v[1]])
+                    st[k] = (None if v[0] is None else torch.empty(v[0].shape, dtype=v[0].dtype, device=dev),
+                             [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in v[1]])
                 else:
-                    db[k] = v
+                    st[k] = v
+            staging[j] = st
+        db = staging[j]
+        with torch.cuda.stream(copy_stream):
+            for k, v in hb.items():
+                if torch.is_tensor(v):
+                    db[k].copy_(v, non_blocking=True)
+                elif k == "itm_plan" and v is not None:
+                    if v[0] is not None:
+                        db[k][0].copy_(v[0], non_blocking=True)
+                    for dst, src in zip(db[k][1], v[1]):
+                        dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return db, ev
@@ -263,11 +277,7 @@ def main():
             j = i % len(schedule)
             if from_host:
                 (batch, ev), nxt = nxt, (prefetch(i + 1) if i + 1 < n_steps else None)
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ev)
-                for v in batch.values():
-                    if torch.is_tensor(v):
-                        v.record_stream(cur)
+                torch.cuda.current_stream().wait_event(ev)
                 lm = step(i, batch).float().mean()         # tiny reduction enqueued behind the step
                 if prev is not None:                       # device -> host read of the previous step's result while this one runs
                     assert np.isfinite(prev.item())
