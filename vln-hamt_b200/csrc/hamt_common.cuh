@@ -67,14 +67,34 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// exact-erf GELU (reference: pretrain_src/model/vilmodel.py:23-29).  erff() is the CUDA libdevice
-// implementation (max 2 ulp); the epilogue is not the bottleneck so no approximation is used.
-__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-based GELU (reference: pretrain_src/model/vilmodel.py:23-29, x * 0.5 * (1 + erf(x / sqrt(2)))).
+// erf is evaluated with Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. below fp32 resolution of the 0.5*(1+erf) factor and
+// five orders of magnitude below the bf16 rounding of the stored result) so that one ex2 + one rcp serve the GEMM epilogue: the
+// libdevice erff() made the GELU / dGELU epilogues 2-3x longer than the tensor-core main loop (profiles/r01_ncu_gemm_shapes.txt).
+// The exponential is shared with the Gaussian pdf needed by the derivative.
+struct ErfParts {
+  float cdf;   // Phi(x) = 0.5 * (1 + erf(x / sqrt 2))
+  float e;     // exp(-x^2 / 2)
+};
+__device__ __forceinline__ ErfParts gauss_cdf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;          // 0.5 * erfc(|x| / sqrt 2)
+  ErfParts r;
+  r.cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  r.e = e;
+  return r;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gauss_cdf(x).cdf; }
 // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const ErfParts g = gauss_cdf(x);
+  return fmaf(x * 0.39894228040143267794f, g.e, g.cdf);
 }
 
 // ---------------------------------------------------------------------------------------------
