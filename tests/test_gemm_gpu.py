@@ -26,7 +26,7 @@ def _tol(K):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (5120, 768, 768), (1024, 2304, 768), (640, 3072, 768),
                                     (333, 1000, 768), (256, 768, 3072), (200, 768, 1000), (77, 37 * 8, 1536)])
-@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("tile_n", [128, 256, 512])
 def test_gemm_forward_bias(M, N, K, tile_n):
     ops = _ops()
     a, b = _rand((M, K), 1), _rand((N, K), 2, 0.05)
@@ -107,6 +107,37 @@ def test_gemm_wgrad_forced_splits_match():
         outs.append(o)
     assert (outs[0] - outs[1]).abs().max().item() < 1e-2
     assert (outs[0] - outs[2]).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 768, 768), (5120, 3072, 768), (300, 768, 3072), (129, 768, 1000)])
+def test_gemm_pair_dgrad_and_epilogues(M, N, K):
+    """CTA-pair kernel (tile_n=512, tcgen05 cta_group::2): MN-major B, dGELU epilogue with prefetched aux, bf16 accumulate."""
+    ops = _ops()
+    dy, w = _rand((M, K), 7), _rand((K, N), 8, 0.05)
+    out = ops.gemm(dy, w, b_mn=True, tile_n=512)
+    ref = dy.float() @ w.float()
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+    pre = _rand((M, N), 11)
+    out2 = ops.gemm(dy, w, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=pre, tile_n=512)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ref2 = ref * x.grad
+    assert (out2.float() - ref2).abs().max().item() <= 2e-2 * ref2.abs().max().item() + 1e-3
+    base = _rand((M, N), 12)
+    acc = base.clone()
+    ops.gemm(dy, w, b_mn=True, out=acc, accumulate=True, tile_n=512)
+    ref3 = ref + base.float()
+    assert (acc.float() - ref3).abs().max().item() <= 3e-2 * ref3.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("Mred,N,K", [(5120, 768, 768), (3392, 3072, 768), (34560, 768, 768), (160, 2304, 768)])
+def test_gemm_pair_wgrad(Mred, N, K):
+    ops = _ops()
+    dy, x = _rand((Mred, N), 12, 0.1), _rand((Mred, K), 13)
+    out = torch.full((N, K), 0.5, dtype=torch.float32, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, accumulate=True, tile_n=512)
+    ref = dy.float().t() @ x.float() + 0.5
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
 
 
 def test_gemm_strided_views():

@@ -21,6 +21,25 @@ def timeit(fn, n=20, warm=5):
     return s.elapsed_time(e) / n
 
 
+def timeit(fn, n=10, warm=2):          # noqa: F811 -- graph-timed: no CPU launch overhead between the n launches
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(3):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / (3 * n)
+
+
 def main():
     res = []
     for (M, N, K) in [(34560, 768, 768), (34560, 2304, 768), (34560, 3072, 768), (34560, 768, 3072), (5120, 768, 768), (5120, 2304, 768),
@@ -29,17 +48,21 @@ def main():
         w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
         row = {"M": M, "N": N, "K": K}
-        for tn in (128, 256):
+        for tn in (128, 256, 512):
             t = timeit(lambda: ops.gemm(a, w, bias=bias, tile_n=tn))
             row[f"fwd_tn{tn}_tflops"] = round(2 * M * N * K / t / 1e9, 1)
-        t = timeit(lambda: torch.nn.functional.linear(a, w, bias.to(torch.bfloat16)))
+        bb = bias.to(torch.bfloat16)
+        t = timeit(lambda: torch.nn.functional.linear(a, w, bb))
         row["torch_tflops"] = round(2 * M * N * K / t / 1e9, 1)
         dy = torch.randn(M, N, device="cuda").to(torch.bfloat16)
-        t = timeit(lambda: ops.gemm(dy, w, b_mn=True))
-        row["dgrad_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        dx = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+        for tn in (0, 512):
+            t = timeit(lambda: ops.gemm(dy, w, b_mn=True, out=dx, tile_n=tn))
+            row[f"dgrad_tn{tn}_tflops"] = round(2 * M * N * K / t / 1e9, 1)
         g = torch.zeros(N, K, device="cuda")
-        t = timeit(lambda: ops.gemm(dy, a, a_mn=True, b_mn=True, out=g, accumulate=True))
-        row["wgrad_tflops"] = round(2 * M * N * K / t / 1e9, 1)
+        for tn in (0, 512):
+            t = timeit(lambda: ops.gemm(dy, a, a_mn=True, b_mn=True, out=g, accumulate=True, tile_n=tn))
+            row[f"wgrad_tn{tn}_tflops"] = round(2 * M * N * K / t / 1e9, 1)
         res.append(row)
         print(json.dumps(row), flush=True)
     # attention

@@ -47,6 +47,8 @@ int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_
   return gemm_bf16(a, (cudaStream_t)stream);
 }
 
+int hamt_gemm_set_auto_pair(int on) { gemm_set_auto_pair(on); return 0; }
+
 int hamt_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd, int M,
                 int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
   return ln_fwd(x, res, gamma, beta, y, z_out, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);

@@ -45,11 +45,13 @@ struct GemmParams {
   float alpha;
 };
 
-template <int BN>
+// PAIR = two CTAs of a cluster run one 256 x BN UMMA (cta_group::2): each stages 128 rows of A and BN/2 rows of B
+template <int BN, bool PAIR = false>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;
+  static constexpr int kStages = (kBRows == 256) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingOffset = kStages * kStageBytes;        // 8 warps x 32 rows x 128 B
   static constexpr int kStagingBytes = kEpiWarps * 32 * 128;
@@ -68,10 +70,14 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
+  constexpr int TM = PAIR ? 2 * BM : BM;            // rows of the output tile owned by one CTA (pair)
+  constexpr int BNL = L::kBRows;                    // B rows staged by this CTA
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   constexpr int kStages = L::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -91,31 +97,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), PAIR ? 2 : 1);         // pair: leader's expect_tx arrive + the peer's remote arrive
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(tempty_bar(s), PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_ptr_addr);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<2 * BN>(tmem_ptr_addr);
+    else tmem_alloc<2 * BN>(tmem_ptr_addr);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                     // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   pdl_grid_sync();   // everything above overlapped the previous kernel; global memory is touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
   const int units = p.tiles_m * p.tiles_n * p.splits;
+  const int u_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int u_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = u_first; u < units; u += u_stride) {
         const int tn = u % p.tiles_n;
         const int tm = (u / p.tiles_n) % p.tiles_m;
         const int sp = u / (p.tiles_n * p.tiles_m);
@@ -125,32 +137,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
-          mbar_expect_tx(full_bar(stage), L::kStageBytes);
-          if (!A_MN) {
-            tma_load_2d(sa, &tma_a, kb * BK, tm * BM, full_bar(stage));
-          } else {
+          const int m_row = tm * TM + (int)rank * BM, n_row = tn * BN + (int)rank * BNL;
+          if (!PAIR) {
+            mbar_expect_tx(full_bar(stage), L::kStageBytes);
+            if (!A_MN) {
+              tma_load_2d(sa, &tma_a, kb * BK, m_row, full_bar(stage));
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tma_a, tm * BM + c * 64, kb * BK, full_bar(stage));
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tma_b, kb * BK, tn * BN, full_bar(stage));
-          } else {
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tma_a, m_row + c * 64, kb * BK, full_bar(stage));
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tma_b, kb * BK, n_row, full_bar(stage));
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tma_b, tn * BN + c * 64, kb * BK, full_bar(stage));
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tma_b, n_row + c * 64, kb * BK, full_bar(stage));
+            }
+          } else {
+            // both CTAs' bytes are counted on the LEADER's full barrier (2 arrivals: leader's expect_tx + peer's plain arrive)
+            const uint32_t lbar = mapa_u32(full_bar(stage), 0);
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+            else mbar_arrive_cluster(lbar);
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &tma_a, kb * BK, m_row, lbar);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * (BK * 128), &tma_a, m_row + c * 64, kb * BK, lbar);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(sb, &tma_b, kb * BK, n_row, lbar);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), &tma_b, n_row + c * 64, kb * BK, lbar);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (pair: the leader CTA issues for both) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = u_first; u < units; u += u_stride) {
         const int sp = u / (p.tiles_n * p.tiles_m);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -169,12 +201,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             // (one TMA box = BK rows * 128 B), SBO = 8 k-rows * 128 B.
             const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (pair: signalled to both CTAs' producers)
+          if (PAIR) umma_commit_pair(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (PAIR) umma_commit_pair(tfull_bar(as), 3); else umma_commit(tfull_bar(as));  // accumulator complete -> epilogue(s)
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -194,17 +228,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const bool aux_vec_ok = p.aux != nullptr && (p.ld_aux & 7) == 0 && ((uintptr_t)p.aux & 15) == 0;
     const bool has_bias = p.bias != nullptr;
     const int r_sub = lane >> 3, c_sub = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 B per instruction
+    const __nv_bfloat16* pre_src = nullptr;
+    long long pre_ld = 0;
+    if (!p.out_f32) {
+      if (p.aux_mode >= 2) { pre_src = p.aux; pre_ld = p.ld_aux; }
+      else if (p.out_mode == 1) { pre_src = reinterpret_cast<const __nv_bfloat16*>(p.out); pre_ld = p.ldo; }
+    }
+    const bool pre_vec_ok = pre_src != nullptr && (pre_ld & 7) == 0 && ((uintptr_t)pre_src & 15) == 0;
+    constexpr int kGroups = (BN / 2) / 64;
 
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = u_first; u < units; u += u_stride) {
       const int tn = u % p.tiles_n;
       const int tm = (u / p.tiles_n) % p.tiles_m;
       if (has_bias) {   // stage this tile's bias slice (double-buffered by accumulator stage)
         if (et < BN) sbias[as * BN + et] = (tn * BN + et < p.N) ? __ldg(p.bias + tn * BN + et) : 0.f;
         epi_bar_sync();
       }
+      const int row0 = tm * TM + (int)rank * BM + quarter * 32;
+      // Operand tiles the epilogue has to READ (saved pre-activation for dGELU/dReLU, or the bf16 gradient it accumulates onto)
+      // are fetched -- coalesced, 4 rows x 128 B per instruction -- BEFORE waiting for the accumulator, so their HBM latency
+      // hides behind the main loop of this tile; the next group's tile is requested while the current one is processed.
+      uint4 pre[8];
+      auto issue_pre = [&](int gI) {
+        const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
+        const int ncols = min(64, p.N - col0);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = row0 + it * 4 + r_sub;
+          uint4 w = make_uint4(0, 0, 0, 0);
+          if (row < p.M && c_sub * 8 < ncols) {
+            const __nv_bfloat16* ap = pre_src + (long long)row * pre_ld + col0 + c_sub * 8;
+            if (pre_vec_ok && c_sub * 8 + 8 <= ncols) w = *reinterpret_cast<const uint4*>(ap);
+            else {
+              __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
+              for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) hw[j] = ap[j];
+            }
+          }
+          pre[it] = w;
+        }
+      };
+      if (pre_src != nullptr) issue_pre(0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row0 = tm * BM + quarter * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * kColsPerWarp);
       const float* bias_t = sbias + as * BN + half * kColsPerWarp;
 
@@ -220,7 +285,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (col0 >= p.N) continue;  // warp-uniform
           float v[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]) * p.alpha; v[32 + j] = __uint_as_float(r1[j]) * p.alpha; }
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] *= p.alpha;
+          }
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
@@ -252,22 +321,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
             __syncwarp();
           } else if (p.aux_mode >= 2) {
-            // gather the aux tile (pre-activation saved by the forward) coalesced, transpose through smem
+            // the aux tile (pre-activation saved by the forward) was prefetched coalesced; transpose it through smem
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + r_sub, row = row0 + r;
-              uint4 w = make_uint4(0, 0, 0, 0);
-              if (row < p.M && c_sub * 8 < ncols) {
-                const __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0 + c_sub * 8;
-                if (aux_vec_ok && c_sub * 8 + 8 <= ncols) w = *reinterpret_cast<const uint4*>(ap);
-                else {
-                  __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
-                  for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) hw[j] = ap[j];
-                }
-              }
-              *reinterpret_cast<uint4*>(stg + stage_off(r, c_sub)) = w;
-            }
+            for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(stg + stage_off(it * 4 + r_sub, c_sub)) = pre[it];
             __syncwarp();
+            if (gI + 1 < kGroups) issue_pre(gI + 1);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(lane, c));
@@ -298,8 +356,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub));
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 8;
               if (out_vec_ok && c_sub * 8 + 8 <= ncols) {
-                if (p.out_mode == 1) {   // gradient accumulation onto a residual-path gradient
-                  const uint4 o = *reinterpret_cast<const uint4*>(op);
+                if (p.out_mode == 1) {   // gradient accumulation onto a residual-path gradient (old values prefetched)
+                  const uint4 o = pre[it];
                   const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, os[4] = {o.x, o.y, o.z, o.w};
                   uint32_t rs[4];
 #pragma unroll
@@ -318,6 +376,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           }
           __syncwarp();
+          if (p.aux_mode < 2 && pre_src != nullptr && gI + 1 < kGroups) issue_pre(gI + 1);   // RMW: old values of the next group
         }
       } else {
         // ---------------- fp32 output: groups of 32 columns (128-byte row segment) ----------------
@@ -372,15 +431,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (!PAIR || leader) mbar_arrive(tempty_bar(as));
+        else mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));   // the leader's MMA issuer owns the accumulator hand-off
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer may still multicast into / arrive on this CTA's barriers until both are done
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,6 +488,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
   return 0;
 }
 
+static bool g_auto_pair = false;   // hamt_gemm_set_auto_pair(): let the cost model pick the CTA-pair kernel
+void gemm_set_auto_pair(int on) { g_auto_pair = on != 0; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -433,10 +501,10 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  using L = SmemLayout<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  using L = SmemLayout<BN, PAIR>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -444,8 +512,21 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     attr_set = true;
   }
   const int units = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = units < num_sms() ? units : num_sms();
-  launch_pdl(kern, grid, kThreads, L::kTotal, st, ta, tb, p);
+  if (!PAIR) {
+    const int grid = units < num_sms() ? units : num_sms();
+    launch_pdl(kern, grid, kThreads, L::kTotal, st, ta, tb, p);
+  } else {
+    const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  }
   return check_launch("gemm_tcgen05_kernel");
 }
 
@@ -459,32 +540,46 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   // Tile width / split-K selection by a small cost model (cycles on one SM; constants from the measured per-k-block
   // MMA time -- 4 x tcgen05.mma 128xBNx16: BN=256 is tensor-bound at 512 cyc, BN=128 is smem-operand-bound at ~330 cyc --
   // and the measured epilogue cost per tile).  waves * unit_time + exposed tail.
+  // tile_n: 0 = auto, 128 / 256 = single-CTA tiles 128 x tile_n, 512 = CTA-pair tile 256 x 256 (cta_group::2)
   int bn = a.tile_n, splits = a.out_mode == 2 ? a.splits : 1;
+  bool pair = false;
   {
-    const int sms = num_sms(), tm = (a.M + BM - 1) / BM;
+    const int sms = num_sms();
     double best = 1e30;
     int best_bn = 128, best_s = 1;
-    for (int cand = 256; cand >= 128; cand -= 128) {
-      if (a.tile_n == 128 || a.tile_n == 256) { if (cand != a.tile_n) continue; }
-      else if (cand == 256 && a.N < 192) continue;
-      const int tn = (a.N + cand - 1) / cand;
-      const double t_kb = cand == 256 ? 540.0 : 330.0, t_epi = (cand == 256 ? 2400.0 : 1300.0) * (a.out_f32 ? 1.6 : 1.0);
+    bool best_pair = false;
+    for (int cand = 0; cand < 3; ++cand) {
+      const int cbn = cand == 0 ? 256 : (cand == 1 ? 256 : 128);
+      const bool cpair = cand == 0;
+      const int code = cpair ? 512 : cbn;
+      if (a.tile_n == 128 || a.tile_n == 256 || a.tile_n == 512) { if (code != a.tile_n) continue; }
+      else {
+        if (cbn == 256 && a.N < 192) continue;
+        if (cpair && (a.M < 256 || !g_auto_pair)) continue;
+      }
+      const int tm = (a.M + (cpair ? 255 : 127)) / (cpair ? 256 : 128), tn = (a.N + cbn - 1) / cbn;
+      const int slots = cpair ? sms / 2 : sms;
+      // cycles per 64-deep k-block of one tile: tensor floor 4 x (128 x BN / 256) per SM; single-CTA tiles are limited by the
+      // L2 -> SM operand traffic when the whole chip runs them (measured ~1.1 PF for 128x256, ~0.75 PF for 128x128)
+      const double t_kb = cpair ? 530.0 : (cbn == 256 ? 620.0 : 340.0);
+      const double t_epi = (cbn == 256 ? 2400.0 : 1300.0) * (a.out_f32 ? 1.6 : 1.0);
       const bool forced = a.out_mode == 2 && a.splits > 0;
       for (int s = forced ? a.splits : 1; s <= (forced ? a.splits : 32); s *= 2) {
         if (a.out_mode != 2 && s > 1) break;
         const int kbs = (p.kb_total + s - 1) / s;
         if (!forced && s > 1 && kbs < 6) break;
         const int units = tm * tn * ((p.kb_total + kbs - 1) / kbs);
-        const int waves = (units + sms - 1) / sms;
+        const int waves = (units + slots - 1) / slots;
         const double unit = kbs * t_kb > t_epi ? kbs * t_kb : t_epi;
         const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0);
-        if (cost < best) { best = cost; best_bn = cand; best_s = s; }
+        if (cost < best) { best = cost; best_bn = cbn; best_s = s; best_pair = cpair; }
       }
     }
     bn = best_bn;
     splits = best_s;
+    pair = best_pair;
   }
-  p.tiles_m = (a.M + BM - 1) / BM;
+  p.tiles_m = (a.M + (pair ? 2 * BM : BM) - 1) / (pair ? 2 * BM : BM);
   p.tiles_n = (a.N + bn - 1) / bn;
   if (splits > p.kb_total) splits = p.kb_total;
   if (splits < 1) splits = 1;
@@ -501,16 +596,17 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   // K-major operand: matrix [rows = M or N, cols = K].  MN-major operand: matrix [rows = K, cols = M or N].
   rc = a.a_mn ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK) : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM);
   if (rc) return rc;
-  rc = a.b_mn ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, bn);
+  rc = a.b_mn ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, pair ? bn / 2 : bn);
   if (rc) return rc;
 
-#define HAMT_DISPATCH(BN_)                                                         \
-  if (!a.a_mn && !a.b_mn) return launch<BN_, false, false>(ta, tb, p, st);        \
-  if (!a.a_mn && a.b_mn) return launch<BN_, false, true>(ta, tb, p, st);          \
-  if (a.a_mn && a.b_mn) return launch<BN_, true, true>(ta, tb, p, st);            \
-  return launch<BN_, true, false>(ta, tb, p, st);
-  if (bn == 256) { HAMT_DISPATCH(256) }
-  HAMT_DISPATCH(128)
+#define HAMT_DISPATCH(BN_, PAIR_)                                                        \
+  if (!a.a_mn && !a.b_mn) return launch<BN_, false, false, PAIR_>(ta, tb, p, st);        \
+  if (!a.a_mn && a.b_mn) return launch<BN_, false, true, PAIR_>(ta, tb, p, st);          \
+  if (a.a_mn && a.b_mn) return launch<BN_, true, true, PAIR_>(ta, tb, p, st);            \
+  return launch<BN_, true, false, PAIR_>(ta, tb, p, st);
+  if (pair) { HAMT_DISPATCH(256, true) }
+  if (bn == 256) { HAMT_DISPATCH(256, false) }
+  HAMT_DISPATCH(128, false)
 #undef HAMT_DISPATCH
 }
 

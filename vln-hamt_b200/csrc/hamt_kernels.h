@@ -19,6 +19,7 @@ struct GemmArgs {
   int splits;                               // 0 = auto (only with out_mode 2)
 };
 int gemm_bf16(const GemmArgs& a, cudaStream_t st);
+void gemm_set_auto_pair(int on);
 
 struct DropArgs { const unsigned long long* seed_ptr; unsigned int site; float p; };
 
