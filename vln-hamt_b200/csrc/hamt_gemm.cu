@@ -97,7 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), PAIR ? 2 : 1);         // pair: leader's expect_tx arrive + the peer's remote arrive
+      mbar_init(full_bar(s), 1);                    // pair: the leader's expect_tx covers the bytes of BOTH CTAs' loads
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -153,10 +153,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               for (int c = 0; c < BNL / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tma_b, n_row + c * 64, kb * BK, full_bar(stage));
             }
           } else {
-            // both CTAs' bytes are counted on the LEADER's full barrier (2 arrivals: leader's expect_tx + peer's plain arrive)
+            // both CTAs' bytes are counted on the LEADER's full barrier, whose single arrival is the leader's expect_tx for
+            // 2 x stage bytes.  (A remote release-arrive from the peer per k-block stalled its producer ~1000 cycles and halved
+            // the MMA rate -- profiles/r01_ncu_pair.txt.)  The peer cannot run a phase ahead: it waits on its own empty barrier,
+            // which the leader's MMA commit signals only after the previous phase of this full barrier has completed.
             const uint32_t lbar = mapa_u32(full_bar(stage), 0);
             if (leader) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
-            else mbar_arrive_cluster(lbar);
             if (!A_MN) {
               tma_load_2d_pair(sa, &tma_a, kb * BK, m_row, lbar);
             } else {
