@@ -43,7 +43,7 @@ int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_
                    int out_mode, int M, int N, int K, const float* bias, int act, int aux_mode, void* aux, long long ld_aux, float alpha,
                    int tile_n, int splits, void* stream);
 
-/* let the tile cost model choose the CTA-pair kernel when tile_n == 0 (off by default until measured faster) */
+/* tile_n == 0: the tile cost model may choose the CTA-pair kernel (default on; 0 restricts it to single-CTA tiles) */
 int hamt_gemm_set_auto_pair(int on);
 
 /* y = LayerNorm(dropout(x) + res) ; BertSelfOutput / BertOutput tail (vilmodel.py:139-143,181-185).

@@ -490,7 +490,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
   return 0;
 }
 
-static bool g_auto_pair = false;   // hamt_gemm_set_auto_pair(): let the cost model pick the CTA-pair kernel
+static bool g_auto_pair = true;    // hamt_gemm_set_auto_pair(0) restricts the cost model to single-CTA tiles
 void gemm_set_auto_pair(int on) { g_auto_pair = on != 0; }
 static int g_num_sms = 0;
 static int num_sms() {
@@ -563,7 +563,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
       const int slots = cpair ? sms / 2 : sms;
       // cycles per 64-deep k-block of one tile: tensor floor 4 x (128 x BN / 256) per SM; single-CTA tiles are limited by the
       // L2 -> SM operand traffic when the whole chip runs them (measured ~1.1 PF for 128x256, ~0.75 PF for 128x128)
-      const double t_kb = cpair ? 530.0 : (cbn == 256 ? 620.0 : 340.0);
+      const double t_kb = cpair ? 540.0 : (cbn == 256 ? 600.0 : 340.0);
       const double t_epi = (cbn == 256 ? 2400.0 : 1300.0) * (a.out_f32 ? 1.6 : 1.0);
       const bool forced = a.out_mode == 2 && a.splits > 0;
       for (int s = forced ? a.splits : 1; s <= (forced ? a.splits : 32); s *= 2) {
@@ -573,7 +573,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
         const int units = tm * tn * ((p.kb_total + kbs - 1) / kbs);
         const int waves = (units + slots - 1) / slots;
         const double unit = kbs * t_kb > t_epi ? kbs * t_kb : t_epi;
-        const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0);
+        const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0) + (cpair ? 1500.0 : 0.0);   // pair: cluster sync + remote hand-offs
         if (cost < best) { best = cost; best_bn = cbn; best_s = s; best_pair = cpair; }
       }
     }
