@@ -271,12 +271,15 @@ def main():
         launches0 = _lib.launch_count()
         e0.record()
         samples, d2h = 0, 0
-        nxt = prefetch(0) if from_host else None
+        DEPTH = 2                                           # batches in flight ahead of the compute (absorbs PCIe / host jitter)
+        queue = [prefetch(k) for k in range(min(DEPTH, n_steps))] if from_host else None
         prev = None
         for i in range(n_steps):
             j = i % len(schedule)
             if from_host:
-                (batch, ev), nxt = nxt, (prefetch(i + 1) if i + 1 < n_steps else None)
+                batch, ev = queue.pop(0)
+                if i + DEPTH < n_steps:
+                    queue.append(prefetch(i + DEPTH))
                 torch.cuda.current_stream().wait_event(ev)
                 lm = step(i, batch).float().mean()         # tiny reduction enqueued behind the step
                 if prev is not None:                       # device -> host read of the previous step's result while this one runs

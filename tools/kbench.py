@@ -83,6 +83,15 @@ def main():
         gm, bt = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
         t = timeit(lambda: ops.ln_fwd(x, r, gm, bt, 1e-12))
         print(json.dumps({"ln_fwd_M": M, "us": round(t * 1e3, 1), "GBs": round(M * 768 * 2 * 4 / t / 1e6, 1)}), flush=True)
+        y, z, mean, rstd = ops.ln_fwd(x.clone(), r, gm, bt, 1e-12)
+        dy = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+        dg, db, dbias = (torch.zeros(768, device="cuda") for _ in range(3))
+        t = timeit(lambda: ops.ln_bwd(dy, z, mean, rstd, gm, dg, db, dbias))
+        print(json.dumps({"ln_bwd_M": M, "us": round(t * 1e3, 1), "GBs": round(M * 768 * 2 * 4 / t / 1e6, 1)}), flush=True)
+        q = torch.randn(M, 2304, device="cuda").to(torch.bfloat16)
+        acc = torch.zeros(2304, device="cuda")
+        t = timeit(lambda: ops.colsum(q, acc))
+        print(json.dumps({"colsum_M": M, "N": 2304, "us": round(t * 1e3, 1), "GBs": round(M * 2304 * 2 / t / 1e6, 1)}), flush=True)
 
 
 if __name__ == "__main__":
