@@ -27,20 +27,6 @@ __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* p, int lane, 
   }
 }
 template <int NCH>
-__device__ __forceinline__ void load_raw(const __nv_bfloat16* p, int lane, uint4 (&w)[NCH]) {
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) w[c] = *reinterpret_cast<const uint4*>(p + c * 256 + lane * 8);
-}
-template <int NCH>
-__device__ __forceinline__ void unpack_raw(const uint4 (&w)[NCH], float (&v)[NCH * 8]) {
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    float2 f0 = unpack_bf16(w[c].x), f1 = unpack_bf16(w[c].y), f2 = unpack_bf16(w[c].z), f3 = unpack_bf16(w[c].w);
-    v[c * 8 + 0] = f0.x; v[c * 8 + 1] = f0.y; v[c * 8 + 2] = f1.x; v[c * 8 + 3] = f1.y;
-    v[c * 8 + 4] = f2.x; v[c * 8 + 5] = f2.y; v[c * 8 + 6] = f3.x; v[c * 8 + 7] = f3.y;
-  }
-}
-template <int NCH>
 __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* p, int lane, const float (&v)[NCH * 8]) {
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
@@ -73,23 +59,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
   float g[NCH * 8], b[NCH * 8];
   load_vec_f32<NCH>(gamma, lane, g);
   load_vec_f32<NCH>(beta, lane, b);
-  // software pipeline: the loads of the next row are in flight while the current row is reduced / normalised / stored
-  const int stride = gridDim.x * wpb;
-  int row = blockIdx.x * wpb + (threadIdx.x >> 5);
-  uint4 rx[NCH], rr[NCH];
-  if (row < M) {
-    load_raw<NCH>(x + (long long)row * H, lane, rx);
-    if (res != nullptr) load_raw<NCH>(res + (long long)row * H, lane, rr);
-  }
-  for (; row < M; row += stride) {
-    uint4 nx[NCH], nr[NCH];
-    const int nrow = row + stride;
-    if (nrow < M) {
-      load_raw<NCH>(x + (long long)nrow * H, lane, nx);
-      if (res != nullptr) load_raw<NCH>(res + (long long)nrow * H, lane, nr);
-    }
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float z[NCH * 8];
-    unpack_raw<NCH>(rx, z);
+    load_row_bf16<NCH>(x + (long long)row * H, lane, z);
     if (ds.on) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
@@ -98,7 +70,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
     }
     if (res != nullptr) {
       float r[NCH * 8];
-      unpack_raw<NCH>(rr, r);
+      load_row_bf16<NCH>(res + (long long)row * H, lane, r);
 #pragma unroll
       for (int i = 0; i < NCH * 8; ++i) z[i] += r[i];
     }
@@ -119,8 +91,6 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
     }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { rx[c] = nx[c]; rr[c] = nr[c]; }
   }
 }
 
@@ -143,29 +113,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   float acc_g[NCH * 8], acc_b[NCH * 8], acc_x[NCH * 8];
 #pragma unroll
   for (int i = 0; i < NCH * 8; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
-  const int stride = gridDim.x * wpb;
-  int row = blockIdx.x * wpb + (threadIdx.x >> 5);
-  uint4 rd[NCH], rz[NCH], ri[NCH];
-  float mean = 0.f, rstd = 0.f;
-  if (row < M) {
-    load_raw<NCH>(dy + (long long)row * H, lane, rd);
-    load_raw<NCH>(z + (long long)row * H, lane, rz);
-    if (dres != nullptr && dres_in != nullptr) load_raw<NCH>(dres_in + (long long)row * H, lane, ri);
-    mean = mean_in[row]; rstd = rstd_in[row];
-  }
-  for (; row < M; row += stride) {
-    uint4 nd[NCH], nz[NCH], ni[NCH];
-    float nmean = 0.f, nrstd = 0.f;
-    const int nrow = row + stride;
-    if (nrow < M) {
-      load_raw<NCH>(dy + (long long)nrow * H, lane, nd);
-      load_raw<NCH>(z + (long long)nrow * H, lane, nz);
-      if (dres != nullptr && dres_in != nullptr) load_raw<NCH>(dres_in + (long long)nrow * H, lane, ni);
-      nmean = mean_in[nrow]; nrstd = rstd_in[nrow];
-    }
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float d[NCH * 8], zz[NCH * 8];
-    unpack_raw<NCH>(rd, d);
-    unpack_raw<NCH>(rz, zz);
+    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
+    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
+    const float mean = mean_in[row], rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH * 8; ++i) {
@@ -186,7 +138,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     if (dres != nullptr) {
       float o[NCH * 8];
       if (dres_in != nullptr) {
-        unpack_raw<NCH>(ri, o);
+        load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
 #pragma unroll
         for (int i = 0; i < NCH * 8; ++i) o[i] += dz[i];
       } else {
@@ -207,9 +159,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
       for (int i = 0; i < NCH * 8; ++i) acc_x[i] += dz[i];
       store_row_bf16<NCH>(dx + (long long)row * H, lane, dz);
     }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { rd[c] = nd[c]; rz[c] = nz[c]; ri[c] = ni[c]; }
-    mean = nmean; rstd = nrstd;
   }
   // cross-warp reduction through shared memory, then one atomic per column per CTA
 #pragma unroll
