@@ -53,15 +53,19 @@ struct AttnP {
   __nv_bfloat16 *dq, *dk, *dv;
 };
 
-// cooperative copy of `rows` x 64 bf16 (row pitch ld) into smem [rows_pad][LDS], zero-filling the padding rows
+// cooperative ASYNC copy (cp.async, 16 B per request, no register round trip: every request of the CTA is in flight at once)
+// of `rows` x 64 bf16 (row pitch ld) into smem [rows_pad][LDS]; padding rows are zero-filled (src-size 0).
 __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows, int rows_pad) {
+  const uint32_t base = smem_u32(dst);
   for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (r < rows) w = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c);
-    *reinterpret_cast<uint4*>(dst + r * LDS + c) = w;
+    const bool valid = r < rows;
+    const __nv_bfloat16* g = valid ? src + (long long)r * ld + c : src;
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + 2u * (uint32_t)(r * LDS + c)), "l"(g), "r"(sz) : "memory");
   }
 }
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
   pdl_grid_sync();
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
   stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
   for (int j = threadIdx.x; j < Sk_pad; j += blockDim.x)
     sMask[j] = j < p.Sk ? (p.mask ? p.mask[(long long)b * p.Sk + j] : 0.f) : -INFINITY;
+  stage_wait();
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -204,18 +209,34 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
   stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
   for (int j = threadIdx.x; j < Sk_pad; j += blockDim.x) sMask[j] = (j < p.Sk && p.mask) ? p.mask[(long long)b * p.Sk + j] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  // delta_i = sum_d dO[i,d] * O[i,d]  (O = saved forward output)
-  for (int i = warp; i < Sq_pad; i += nwarps) {
-    float acc = 0.f;
-    if (i < p.Sq) {
-      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.dout + b * p.do_bs + (long long)i * p.lddo + h * D + lane * 2));
-      const float2 o = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.out + b * p.o_bs + (long long)i * p.ldo + h * D + lane * 2));
-      acc = a.x * o.x + a.y * o.y;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      sDelta[i] = acc;
-      sLse[i] = i < p.Sq ? p.lse[((long long)b * p.heads + h) * p.Sq + i] : 0.f;
+  // delta_i = sum_d dO[i,d] * O[i,d]  (O = saved forward output).  Item = (row, 16-byte chunk): the O chunks are requested
+  // from global memory while the cp.async staging is still in flight; at most 4 items per thread (blockDim >= Sq_pad * 2).
+  uint4 o_reg[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int item = threadIdx.x + k * blockDim.x, r = item >> 3, c = (item & 7) * 8;
+    o_reg[k] = make_uint4(0, 0, 0, 0);
+    if (item < Sq_pad * 8 && r < p.Sq) o_reg[k] = *reinterpret_cast<const uint4*>(p.out + b * p.o_bs + (long long)r * p.ldo + h * D + c);
+  }
+  for (int i = threadIdx.x; i < Sq_pad; i += blockDim.x) sLse[i] = i < p.Sq ? p.lse[((long long)b * p.heads + h) * p.Sq + i] : 0.f;
+  stage_wait();
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int item = threadIdx.x + k * blockDim.x, r = item >> 3, c = (item & 7) * 8;
+    if (item < Sq_pad * 8) {                     // whole warps are in or out (Sq_pad * 8 and blockDim are multiples of 32)
+      const uint4 d4 = *reinterpret_cast<const uint4*>(sDO + r * LDS + c);
+      const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, ow[4] = {o_reg[k].x, o_reg[k].y, o_reg[k].z, o_reg[k].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = unpack_bf16(dw[q]), o = unpack_bf16(ow[q]);
+        acc += a.x * o.x + a.y * o.y;
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if ((item & 7) == 0) sDelta[r] = acc;
     }
   }
   __syncthreads();
