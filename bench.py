@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--dp-mode", default="overlap", choices=["graph", "after", "overlap"],
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
+    ap.add_argument("--diag", action="store_true", help="print the e2e host-time breakdown and the per-signature GEMM table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -265,7 +266,11 @@ def main():
             ev.record(copy_stream)
         return db, ev
 
-    def timed(n_steps, from_host):
+    diag_t = {"prefetch": 0.0, "step": 0.0, "item": 0.0}
+
+    def timed(n_steps, from_host, read_loss=True, copy=True):
+        for k in diag_t:
+            diag_t[k] = 0.0
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = _lib.launch_count()
@@ -277,15 +282,20 @@ def main():
         for i in range(n_steps):
             j = i % len(schedule)
             if from_host:
+                t0 = time.perf_counter()
                 batch, ev = queue.pop(0)
                 if i + DEPTH < n_steps:
-                    queue.append(prefetch(i + DEPTH))
+                    queue.append(prefetch(i + DEPTH) if copy else (staging[(i + DEPTH) % len(schedule)], ev))
                 torch.cuda.current_stream().wait_event(ev)
+                t1 = time.perf_counter()
                 lm = step(i, batch).float().mean()         # tiny reduction enqueued behind the step
-                if prev is not None:                       # device -> host read of the previous step's result while this one runs
+                t2 = time.perf_counter()
+                if prev is not None and read_loss:         # device -> host read of the previous step's result while this one runs
                     assert np.isfinite(prev.item())
                     d2h += 4
                 prev = lm
+                t3 = time.perf_counter()
+                diag_t["prefetch"] += t1 - t0; diag_t["step"] += t2 - t1; diag_t["item"] += t3 - t2
             else:
                 step(i, dev_batches[j])
             samples += batch_size_of(schedule[j], B)
@@ -314,6 +324,15 @@ def main():
     ms, samples, launches, _ = timed(args.steps, from_host=False)
     clocks = sampler.result()
     ms_e2e, samples_e2e, _, d2h = timed(args.steps, from_host=True)
+    if args.diag and rank == 0:
+        print(f"[diag] e2e {ms_e2e / args.steps:.2f} ms/step; host ms/step: " + ", ".join(f"{k}={v / args.steps * 1e3:.2f}" for k, v in diag_t.items()), file=sys.stderr)
+        m2, _, _, _ = timed(args.steps, from_host=True, read_loss=False)
+        print(f"[diag] e2e without per-step loss read: {m2 / args.steps:.2f} ms/step; host: " + ", ".join(f"{k}={v / args.steps * 1e3:.2f}" for k, v in diag_t.items()), file=sys.stderr)
+        m3, _, _, _ = timed(args.steps, from_host=True, copy=False)
+        print(f"[diag] e2e without H2D copies (staging reused): {m3 / args.steps:.2f} ms/step; host: " + ", ".join(f"{k}={v / args.steps * 1e3:.2f}" for k, v in diag_t.items()), file=sys.stderr)
+        t0 = time.perf_counter()
+        m4, _, _, _ = timed(args.steps, from_host=False)
+        print(f"[diag] device-resident again: {m4 / args.steps:.2f} ms/step, host wall {1e3 * (time.perf_counter() - t0) / args.steps:.2f} ms/step", file=sys.stderr)
     n_graphs1 = len(trainer.steps) if trainer else 0
     # copy-only leg: how long the per-step host->device transfer takes on this box when nothing else runs
     torch.cuda.synchronize()
@@ -370,6 +389,9 @@ def main():
         t_us = e0.elapsed_time(e1) * 1e3 / REP
         gemm_flops += cnt * 2.0 * sig[0] * sig[1] * sig[2]
         gemm_us += cnt * t_us
+        if args.diag and rank == 0:
+            print(f"[gemm] M={sig[0]:6d} N={sig[1]:6d} K={sig[2]:6d} a_mn={int(sig[3])} b_mn={int(sig[4])} act={sig[5]} aux={sig[6]} acc={int(sig[7])} {sig[8][6:]:8s} "
+                  f"n={cnt:4d} us={t_us:8.1f} TF={2.0 * sig[0] * sig[1] * sig[2] / t_us / 1e6:7.1f} tot_ms={cnt * t_us / 1e3:7.3f}", file=sys.stderr)
         n_gemm += cnt
         del g
     calls.clear()

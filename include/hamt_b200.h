@@ -38,10 +38,12 @@ long long hamt_launch_count(void);
  * out_f32: 0 bf16 / 1 fp32 output.  out_mode: 0 store, 1 out += , 2 out += with split-K atomics.
  * act: 0 none, 1 exact-erf GELU (vilmodel.py:23-29), 2 ReLU (pretrain_cmt.py:16).
  * aux_mode: 0 none, 1 also store the pre-activation (bf16) to aux, 2 multiply by dGELU(aux), 3 by (aux > 0).
- * tile_n: 0 auto / 128 / 256 (one CTA per 128 x tile_n tile) / 512 (CTA pair, 256 x 256 tile, tcgen05 cta_group::2).  splits: 0 auto. */
+ * tile_n: 0 auto / 128 / 256 (one CTA per 128 x tile_n tile) / 512 (CTA pair, 256 x 256 tile, tcgen05 cta_group::2).  splits: 0 auto.
+ * colsum: fp32 [N] or null; the epilogue ACCUMULATES the column sums of the stored bf16 output into it -- the bias gradient of
+ *   the Linear that produced the activation whose gradient this GEMM writes (replaces a separate pass over [M,N]); bf16 store only. */
 int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out, long long ldo, int out_f32,
                    int out_mode, int M, int N, int K, const float* bias, int act, int aux_mode, void* aux, long long ld_aux, float alpha,
-                   int tile_n, int splits, void* stream);
+                   int tile_n, int splits, float* colsum, void* stream);
 
 /* tile_n == 0: the tile cost model may choose the CTA-pair kernel (default on; 0 restricts it to single-CTA tiles) */
 int hamt_gemm_set_auto_pair(int on);

@@ -159,3 +159,33 @@ def test_gemm_rejects_bad_pitch():
     b = _rand((64, 99), 19)
     with pytest.raises((RuntimeError, ValueError)):
         ops.gemm(a, b)
+
+
+def test_gemm_gelu_epilogue_accuracy():
+    """The single-ex2 Gaussian-cdf polynomial of the GELU epilogue: |gelu error| well below bf16 resolution.  fp32 accumulate of
+    identity-like operands isolates the activation: out = gelu(bias) exactly up to the final bf16 rounding."""
+    ops = _ops()
+    N = 4096
+    xs = torch.linspace(-9.0, 9.0, N).cuda()
+    a = torch.zeros((128, 64), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros((N, 64), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, b, bias=xs, act=ops.ACT_GELU, out_dtype=torch.bfloat16)
+    ref = torch.nn.functional.gelu(xs.double()).float()
+    got = out[0].float()
+    # within half a bf16 ulp of the exact value (ulp <= |v| * 2^-7) + 1e-5 absolute for the polynomial
+    assert ((got - ref).abs() <= ref.abs() * 2.0 ** -8 + 1e-5).all(), f"max |err| {(got - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(384, 3072, 768, 0), (5120, 3072, 768, 512), (333, 1000, 768, 256), (129, 776, 192, 128)])
+def test_gemm_fused_colsum(M, N, K, tile_n):
+    """colsum: the dgrad epilogue accumulates the column sums of the stored bf16 output (bias gradient of the producing Linear,
+    vilmodel.py:168-171 backward) -- must equal a separate pass over the output."""
+    ops = _ops()
+    dy, w = _rand((M, K), 21), _rand((K, N), 22, 0.05)
+    pre = _rand((M, N), 23)
+    cs = torch.full((N,), 0.25, dtype=torch.float32, device="cuda")
+    out = ops.gemm(dy, w, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=pre, colsum=cs, tile_n=tile_n)
+    ref = out.float().sum(0) + 0.25
+    assert (cs - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()) + 1e-3
+    out2 = ops.gemm(dy, w, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=pre, tile_n=tile_n)
+    assert torch.equal(out, out2)

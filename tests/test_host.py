@@ -39,7 +39,7 @@ def test_invalid_arguments_are_reported_not_crashing():
     import hamt_b200  # noqa: F401
     from hamt_b200 import _lib
     lib = _lib.load()
-    assert lib.hamt_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, 0, 0, 0, 0, None, 0, 0, None, 0, 1.0, 0, 0, None) != 0
+    assert lib.hamt_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, 0, 0, 0, 0, None, 0, 0, None, 0, 1.0, 0, 0, None, None) != 0
     assert "empty" in _lib.last_error()
     assert lib.hamt_ln_fwd(None, None, None, None, None, None, None, None, 4, 100, 1e-12, None, 0, 0.0, None) != 0
     assert "hidden size" in _lib.last_error()

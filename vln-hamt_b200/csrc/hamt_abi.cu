@@ -42,8 +42,8 @@ long long hamt_launch_count(void) { return g_launches.load(); }
 
 int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, void* out, long long ldo, int out_f32,
                    int out_mode, int M, int N, int K, const float* bias, int act, int aux_mode, void* aux, long long ld_aux, float alpha,
-                   int tile_n, int splits, void* stream) {
-  GemmArgs a{A, a_mn, lda, B, b_mn, ldb, out, ldo, out_f32, out_mode, M, N, K, bias, act, aux_mode, aux, ld_aux, alpha, tile_n, splits};
+                   int tile_n, int splits, float* colsum, void* stream) {
+  GemmArgs a{A, a_mn, lda, B, b_mn, ldb, out, ldo, out_f32, out_mode, M, N, K, bias, act, aux_mode, aux, ld_aux, alpha, tile_n, splits, colsum};
   return gemm_bf16(a, (cudaStream_t)stream);
 }
 

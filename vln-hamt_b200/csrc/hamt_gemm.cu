@@ -43,6 +43,7 @@ struct GemmParams {
   __nv_bfloat16* aux;
   long long ld_aux;
   float alpha;
+  float* colsum;      // [N] fp32 or null: += column sums of the bf16 output (bias gradient of the producing Linear)
 };
 
 // PAIR = two CTAs of a cluster run one 256 x BN UMMA (cta_group::2): each stages 128 rows of A and BN/2 rows of B
@@ -70,7 +71,19 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+// epilogue specialisations (EPI template argument)
+enum : int {
+  EPI_GENERIC = 0,    // every option decided at run time (heads: ReLU / dReLU, odd combinations)
+  EPI_STORE = 1,      // bf16 store (+ bias)
+  EPI_GELU_PRE = 2,   // bf16 store of gelu(acc + bias), pre-activation stored to aux        (BertIntermediate forward)
+  EPI_DGELU = 3,      // bf16 store of acc * gelu'(aux) (+ fused column sums)                 (BertOutput dgrad)
+  EPI_ACCUM = 4,      // bf16 out += acc                                                      (dgrad onto the residual-path gradient)
+  EPI_F32 = 5         // fp32 store / RMW / split-K red                                       (wgrad, logits)
+};
+
+// 320 threads, one CTA per SM: __launch_bounds__(320, 1) would cap ptxas at 168 registers (it sizes for 384 threads) and the
+// dGELU / accumulate epilogues spilled; 200 x 320 = 64 000 registers still fit the 64 K file.
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using L = SmemLayout<BN, PAIR>;
@@ -216,6 +229,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     // ===================== epilogue warps =====================
+    // The epilogue is specialised at compile time (EPI) for the combinations the hot path runs thousands of times per step, so
+    // each instantiation carries only its own straight-line code: the one-size-fits-all version was ~4 k SASS instructions and
+    // lost a quarter of its issue slots to instruction-cache misses (profiles/r01_ncu_gelu_epilogue.txt, stall_no_inst 24 %).
+    // Interior tiles (all 32 rows of the warp's slab < M, full 128-byte column group, 16-byte aligned pitches) take a
+    // predicate-free path; edge tiles run compact rolled loops with scalar accesses.
+    constexpr bool GEN = EPI == EPI_GENERIC;
     const int e = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int half = e >> 2;               // which half of the BN columns
@@ -225,16 +244,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     float* sbias = reinterpret_cast<float*>(smem_raw + L::kBiasOffset);
     int as = 0;
     uint32_t aphase = 0;
-    const int esz = p.out_f32 ? 4 : 2;
+    const bool out_f32 = GEN ? (p.out_f32 != 0) : (EPI == EPI_F32);
+    const int act = GEN ? p.act : (EPI == EPI_GELU_PRE ? 1 : 0);
+    const int aux_mode = GEN ? p.aux_mode : (EPI == EPI_GELU_PRE ? 1 : (EPI == EPI_DGELU ? 2 : 0));
+    const int out_mode = (GEN || EPI == EPI_F32) ? p.out_mode : (EPI == EPI_ACCUM ? 1 : 0);
+    const bool do_colsum = (GEN || EPI == EPI_DGELU) && p.colsum != nullptr;
+    const bool use_alpha = (GEN || EPI == EPI_F32) && p.alpha != 1.0f;
+    const int esz = out_f32 ? 4 : 2;
     const bool out_vec_ok = (((uintptr_t)p.out & 15) == 0) && ((p.ldo * esz) % 16 == 0);
     const bool aux_vec_ok = p.aux != nullptr && (p.ld_aux & 7) == 0 && ((uintptr_t)p.aux & 15) == 0;
     const bool has_bias = p.bias != nullptr;
     const int r_sub = lane >> 3, c_sub = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 B per instruction
-    const __nv_bfloat16* pre_src = nullptr;
+    const __nv_bfloat16* pre_src = nullptr;          // bf16 tile the epilogue has to READ: saved pre-activation, or the old gradient
     long long pre_ld = 0;
-    if (!p.out_f32) {
-      if (p.aux_mode >= 2) { pre_src = p.aux; pre_ld = p.ld_aux; }
-      else if (p.out_mode == 1) { pre_src = reinterpret_cast<const __nv_bfloat16*>(p.out); pre_ld = p.ldo; }
+    if (!out_f32) {
+      if (aux_mode >= 2) { pre_src = p.aux; pre_ld = p.ld_aux; }
+      else if (out_mode == 1) { pre_src = reinterpret_cast<const __nv_bfloat16*>(p.out); pre_ld = p.ldo; }
     }
     const bool pre_vec_ok = pre_src != nullptr && (pre_ld & 7) == 0 && ((uintptr_t)pre_src & 15) == 0;
     constexpr int kGroups = (BN / 2) / 64;
@@ -247,27 +272,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         epi_bar_sync();
       }
       const int row0 = tm * TM + (int)rank * BM + quarter * 32;
-      // Operand tiles the epilogue has to READ (saved pre-activation for dGELU/dReLU, or the bf16 gradient it accumulates onto)
-      // are fetched -- coalesced, 4 rows x 128 B per instruction -- BEFORE waiting for the accumulator, so their HBM latency
-      // hides behind the main loop of this tile; the next group's tile is requested while the current one is processed.
-      uint4 pre[8];
-      auto issue_pre = [&](int gI) {
-        const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
-        const int ncols = min(64, p.N - col0);
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = row0 + it * 4 + r_sub;
-          uint4 w = make_uint4(0, 0, 0, 0);
-          if (row < p.M && c_sub * 8 < ncols) {
-            const __nv_bfloat16* ap = pre_src + (long long)row * pre_ld + col0 + c_sub * 8;
-            if (pre_vec_ok && c_sub * 8 + 8 <= ncols) w = *reinterpret_cast<const uint4*>(ap);
-            else {
-              __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
-              for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) hw[j] = ap[j];
-            }
+      const bool rows_full = row0 + 32 <= p.M;
+      // guarded 16-byte chunk accessors for edge tiles (row / column bounds, unaligned pitches)
+      auto load_chunk = [&](const __nv_bfloat16* base, long long ld, bool vec, int row, int col, int nvalid) -> uint4 {
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (row < p.M && nvalid > 0) {
+          const __nv_bfloat16* ap = base + (long long)row * ld + col;
+          if (vec && nvalid >= 8) w = *reinterpret_cast<const uint4*>(ap);
+          else {
+            __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
+            for (int j = 0; j < 8 && j < nvalid; ++j) hw[j] = ap[j];
           }
-          pre[it] = w;
         }
+        return w;
+      };
+      auto store_chunk = [&](__nv_bfloat16* base, long long ld, bool vec, int row, int col, int nvalid, uint4 w) {
+        if (row < p.M && nvalid > 0) {
+          __nv_bfloat16* ap = base + (long long)row * ld + col;
+          if (vec && nvalid >= 8) *reinterpret_cast<uint4*>(ap) = w;
+          else {
+            const __nv_bfloat16* hw = reinterpret_cast<const __nv_bfloat16*>(&w);
+            for (int j = 0; j < 8 && j < nvalid; ++j) ap[j] = hw[j];
+          }
+        }
+      };
+      // Operand tiles the epilogue has to READ are fetched -- coalesced, 4 rows x 128 B per instruction -- BEFORE waiting for the
+      // accumulator, so their HBM latency hides behind the main loop of this tile; the next group's tile is requested while the
+      // current one is processed.  (Interior tiles only; edge tiles load at the point of use.)
+      uint4 pre[8];
+      auto group_fast = [&](int gI) {
+        const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
+        return rows_full && col0 + 64 <= p.N && out_vec_ok && (pre_src == nullptr || pre_vec_ok) && (aux_mode != 1 || aux_vec_ok);
+      };
+      auto issue_pre = [&](int gI) {
+        if (!group_fast(gI)) return;
+        const __nv_bfloat16* ap = pre_src + (long long)(row0 + r_sub) * pre_ld + tn * BN + half * kColsPerWarp + gI * 64 + c_sub * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) pre[it] = *reinterpret_cast<const uint4*>(ap + (long long)(it * 4) * pre_ld);
       };
       if (pre_src != nullptr) issue_pre(0);
       mbar_wait(tfull_bar(as), aphase);
@@ -275,20 +316,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * kColsPerWarp);
       const float* bias_t = sbias + as * BN + half * kColsPerWarp;
 
-      if (!p.out_f32) {
+      if (!out_f32) {
         // ---------------- bf16 output: groups of 64 columns (one 128-byte row segment) ----------------
 #pragma unroll 1
-        for (int gI = 0; gI < kColsPerWarp / 64; ++gI) {
+        for (int gI = 0; gI < kGroups; ++gI) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(t_row + gI * 64, r0);
           tmem_ld_32x32(t_row + gI * 64 + 32, r1);
           tmem_ld_wait();
           const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
           if (col0 >= p.N) continue;  // warp-uniform
+          const bool fast = group_fast(gI);
+          const int ncols = min(64, p.N - col0);
           float v[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-          if (p.alpha != 1.0f) {
+          if (use_alpha) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] *= p.alpha;
           }
@@ -299,8 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           }
-          const int ncols = min(64, p.N - col0);
-          if (p.aux_mode == 1) {
+          if (aux_mode == 1) {
             // also emit the pre-activation (needed by the dGELU / dReLU backward)
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -308,24 +350,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
                              pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
             __syncwarp();
+            if (fast) {
+              __nv_bfloat16* ap = p.aux + (long long)(row0 + r_sub) * p.ld_aux + col0 + c_sub * 8;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + r_sub, row = row0 + r;
-              if (row < p.M && c_sub * 8 < ncols) {
-                const uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub));
-                __nv_bfloat16* ap = p.aux + (long long)row * p.ld_aux + col0 + c_sub * 8;
-                if (aux_vec_ok && c_sub * 8 + 8 <= ncols) *reinterpret_cast<uint4*>(ap) = w;
-                else {
-                  const __nv_bfloat16* hw = reinterpret_cast<const __nv_bfloat16*>(&w);
-                  for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) ap[j] = hw[j];
-                }
+              for (int it = 0; it < 8; ++it)
+                *reinterpret_cast<uint4*>(ap + (long long)(it * 4) * p.ld_aux) = *reinterpret_cast<const uint4*>(stg + stage_off(it * 4 + r_sub, c_sub));
+            } else {
+#pragma unroll 1
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + r_sub;
+                store_chunk(p.aux, p.ld_aux, aux_vec_ok, row0 + r, col0 + c_sub * 8, ncols - c_sub * 8, *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub)));
               }
             }
             __syncwarp();
-          } else if (p.aux_mode >= 2) {
-            // the aux tile (pre-activation saved by the forward) was prefetched coalesced; transpose it through smem
+          } else if (aux_mode >= 2) {
+            // the aux tile (pre-activation saved by the forward) goes through smem so that every lane gets its own row
+            if (fast) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(stg + stage_off(it * 4 + r_sub, c_sub)) = pre[it];
+              for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(stg + stage_off(it * 4 + r_sub, c_sub)) = pre[it];
+            } else {
+#pragma unroll 1
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + r_sub;
+                *reinterpret_cast<uint4*>(stg + stage_off(r, c_sub)) = load_chunk(pre_src, pre_ld, pre_vec_ok, row0 + r, col0 + c_sub * 8, ncols - c_sub * 8);
+              }
+            }
             __syncwarp();
             if (gI + 1 < kGroups) issue_pre(gI + 1);
 #pragma unroll
@@ -334,14 +383,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
               const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[c * 8 + j] = p.aux_mode == 2 ? v[c * 8 + j] * dgelu_erf(a[j]) : (a[j] > 0.f ? v[c * 8 + j] : 0.f);
+              for (int j = 0; j < 8; ++j) v[c * 8 + j] = aux_mode == 2 ? v[c * 8 + j] * dgelu_erf(a[j]) : (a[j] > 0.f ? v[c * 8 + j] : 0.f);
             }
             __syncwarp();
           }
-          if (p.act == 1) {
+          if (act == 1) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == 2) {
+          } else if (act == 2) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
           }
@@ -351,34 +400,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
                            pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
           __syncwarp();
+          float cs[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + r_sub, row = row0 + r;
-            if (row < p.M && c_sub * 8 < ncols) {
+          for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+          auto add_bf16x8 = [](uint4 a, uint4 b) {
+            const uint32_t as_[4] = {a.x, a.y, a.z, a.w}, bs_[4] = {b.x, b.y, b.z, b.w};
+            uint32_t rs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 x = unpack_bf16(as_[k]), y = unpack_bf16(bs_[k]);
+              rs[k] = pack_bf16(x.x + y.x, x.y + y.y);
+            }
+            return make_uint4(rs[0], rs[1], rs[2], rs[3]);
+          };
+          auto acc_cs = [&](uint4 w) {   // column sums of exactly the bf16 values a separate pass over the output would read
+            const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+            cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y; cs[4] += f2.x; cs[5] += f2.y; cs[6] += f3.x; cs[7] += f3.y;
+          };
+          if (fast) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)(row0 + r_sub) * p.ldo + col0 + c_sub * 8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(it * 4 + r_sub, c_sub));
+              if (do_colsum) acc_cs(w);
+              if (out_mode == 1) w = add_bf16x8(w, pre[it]);   // gradient accumulation onto a residual-path gradient (old values prefetched)
+              *reinterpret_cast<uint4*>(op + (long long)(it * 4) * p.ldo) = w;
+            }
+          } else {
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + r_sub, row = row0 + r, nvalid = ncols - c_sub * 8;
               uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off(r, c_sub));
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 8;
-              if (out_vec_ok && c_sub * 8 + 8 <= ncols) {
-                if (p.out_mode == 1) {   // gradient accumulation onto a residual-path gradient (old values prefetched)
-                  const uint4 o = pre[it];
-                  const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, os[4] = {o.x, o.y, o.z, o.w};
-                  uint32_t rs[4];
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const float2 a = unpack_bf16(ws[k]), b = unpack_bf16(os[k]);
-                    rs[k] = pack_bf16(a.x + b.x, a.y + b.y);
+              if (row < p.M && nvalid > 0) {
+                if (do_colsum) {
+                  if (nvalid < 8) {   // zero the lanes beyond N so the scalar tail below adds nothing for them
+                    __nv_bfloat16* hw = reinterpret_cast<__nv_bfloat16*>(&w);
+                    for (int j = nvalid; j < 8; ++j) hw[j] = __float2bfloat16_rn(0.f);
                   }
-                  w = make_uint4(rs[0], rs[1], rs[2], rs[3]);
+                  acc_cs(w);
                 }
-                *reinterpret_cast<uint4*>(op) = w;
+                if (out_mode == 1) w = add_bf16x8(w, load_chunk(reinterpret_cast<const __nv_bfloat16*>(p.out), p.ldo, out_vec_ok, row, col0 + c_sub * 8, nvalid));
+                store_chunk(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, out_vec_ok, row, col0 + c_sub * 8, nvalid, w);
+              }
+            }
+          }
+          if (do_colsum) {      // warp-uniform
+            // rows of this warp's 32 x 64 slab: 8 per thread above, then across the 4 row sub-groups (lane bits 3, 4)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+              cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+            }
+            if (r_sub == 0 && c_sub * 8 < ncols) {
+              float* cp = p.colsum + col0 + c_sub * 8;
+              if (c_sub * 8 + 8 <= ncols && (((uintptr_t)cp) & 15) == 0) {
+                red_add_v4(cp, cs[0], cs[1], cs[2], cs[3]);
+                red_add_v4(cp + 4, cs[4], cs[5], cs[6], cs[7]);
               } else {
-                const __nv_bfloat16* hw = reinterpret_cast<const __nv_bfloat16*>(&w);
-                for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j)
-                  op[j] = p.out_mode == 1 ? __float2bfloat16_rn(__bfloat162float(hw[j]) + __bfloat162float(op[j])) : hw[j];
+                for (int j = 0; j < 8 && c_sub * 8 + j < ncols; ++j) atomicAdd(cp + j, cs[j]);
               }
             }
           }
           __syncwarp();
-          if (p.aux_mode < 2 && pre_src != nullptr && gI + 1 < kGroups) issue_pre(gI + 1);   // RMW: old values of the next group
+          if (aux_mode < 2 && pre_src != nullptr && gI + 1 < kGroups) issue_pre(gI + 1);   // RMW: old values of the next group
         }
       } else {
         // ---------------- fp32 output: groups of 32 columns (128-byte row segment) ----------------
@@ -390,40 +474,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const int col0 = tn * BN + half * kColsPerWarp + gI * 32;
           if (col0 >= p.N) continue;
           const int ncols = min(32, p.N - col0);
+          const bool fast = rows_full && ncols == 32 && out_vec_ok;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) * p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+          if (use_alpha) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bias_t[gI * 32 + j];
           }
-          if (p.act == 1) {
+          if (GEN || EPI == EPI_F32) {
+            if (act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == 2) {
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (act == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(stg + stage_off(lane, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
           __syncwarp();
+          if (fast) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)(row0 + r_sub) * p.ldo + col0 + c_sub * 4;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + r_sub, row = row0 + r;
-            if (row < p.M && c_sub * 4 < ncols) {
-              float4 w = *reinterpret_cast<const float4*>(stg + stage_off(r, c_sub));
-              float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 4;
-              if (out_vec_ok && c_sub * 4 + 4 <= ncols) {
-                if (p.out_mode == 2) red_add_v4(op, w.x, w.y, w.z, w.w);
-                else {
-                  if (p.out_mode == 1) { const float4 o = *reinterpret_cast<const float4*>(op); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
-                  *reinterpret_cast<float4*>(op) = w;
-                }
-              } else {
-                const float ws[4] = {w.x, w.y, w.z, w.w};
-                for (int j = 0; j < 4 && c_sub * 4 + j < ncols; ++j) {
-                  if (p.out_mode == 2) atomicAdd(op + j, ws[j]);
-                  else op[j] = (p.out_mode == 1 ? op[j] : 0.f) + ws[j];
+            for (int it = 0; it < 8; ++it) {
+              float4 w = *reinterpret_cast<const float4*>(stg + stage_off(it * 4 + r_sub, c_sub));
+              float* o = op + (long long)(it * 4) * p.ldo;
+              if (out_mode == 2) red_add_v4(o, w.x, w.y, w.z, w.w);
+              else {
+                if (out_mode == 1) { const float4 q = *reinterpret_cast<const float4*>(o); w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w; }
+                *reinterpret_cast<float4*>(o) = w;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + r_sub, row = row0 + r;
+              if (row < p.M && c_sub * 4 < ncols) {
+                const float4 w = *reinterpret_cast<const float4*>(stg + stage_off(r, c_sub));
+                float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0 + c_sub * 4;
+                if (out_vec_ok && c_sub * 4 + 4 <= ncols) {
+                  if (out_mode == 2) red_add_v4(op, w.x, w.y, w.z, w.w);
+                  else {
+                    float4 q = w;
+                    if (out_mode == 1) { const float4 o = *reinterpret_cast<const float4*>(op); q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w; }
+                    *reinterpret_cast<float4*>(op) = q;
+                  }
+                } else {
+                  const float ws[4] = {w.x, w.y, w.z, w.w};
+                  for (int j = 0; j < 4 && c_sub * 4 + j < ncols; ++j) {
+                    if (out_mode == 2) atomicAdd(op + j, ws[j]);
+                    else op[j] = (out_mode == 1 ? op[j] : 0.f) + ws[j];
+                  }
                 }
               }
             }
@@ -503,10 +609,10 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<BN, PAIR>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -591,7 +697,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   p.out_mode = (a.out_mode == 2 && p.splits == 1) ? 1 : a.out_mode;
   p.bias = a.bias; p.act = a.act; p.aux_mode = a.aux_mode; p.aux = (__nv_bfloat16*)a.aux; p.ld_aux = a.ld_aux;
   p.alpha = a.alpha;
+  p.colsum = a.colsum;
+  HAMT_REQUIRE(a.colsum == nullptr || (!a.out_f32 && a.out_mode == 0), "gemm: colsum needs a plainly stored bf16 output");
   HAMT_REQUIRE(p.aux_mode == 0 || p.aux != nullptr, "gemm: aux_mode set without aux buffer");
+  HAMT_REQUIRE(!(p.aux_mode >= 2 && p.out_mode != 0), "gemm: the dGELU / dReLU epilogues store, they do not accumulate");
 
   CUtensorMap ta, tb;
   int rc;
@@ -601,14 +710,37 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   rc = a.b_mn ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, pair ? bn / 2 : bn);
   if (rc) return rc;
 
-#define HAMT_DISPATCH(BN_, PAIR_)                                                        \
-  if (!a.a_mn && !a.b_mn) return launch<BN_, false, false, PAIR_>(ta, tb, p, st);        \
-  if (!a.a_mn && a.b_mn) return launch<BN_, false, true, PAIR_>(ta, tb, p, st);          \
-  if (a.a_mn && a.b_mn) return launch<BN_, true, true, PAIR_>(ta, tb, p, st);            \
-  return launch<BN_, true, false, PAIR_>(ta, tb, p, st);
+  // epilogue specialisation: the combinations the transformer blocks run; everything else takes the generic kernel
+  int epi = EPI_GENERIC;
+  if (p.out_f32) { if (p.act == 0 && p.aux_mode == 0 && p.colsum == nullptr) epi = EPI_F32; }
+  else if (p.alpha == 1.0f) {
+    if (p.act == 0 && p.aux_mode == 0 && p.colsum == nullptr) epi = p.out_mode == 0 ? EPI_STORE : (p.out_mode == 1 ? EPI_ACCUM : EPI_GENERIC);
+    else if (p.act == 1 && p.aux_mode == 1 && p.out_mode == 0 && p.colsum == nullptr) epi = EPI_GELU_PRE;
+    else if (p.act == 0 && p.aux_mode == 2 && p.out_mode == 0) epi = EPI_DGELU;
+  }
+#define HAMT_LAUNCH(BN_, AMN_, BMN_, PAIR_, EPI_) return launch<BN_, AMN_, BMN_, PAIR_, EPI_>(ta, tb, p, st);
+#define HAMT_DISPATCH(BN_, PAIR_)                                                                    \
+  if (!a.a_mn && !a.b_mn) {                                                                          \
+    if (epi == EPI_STORE) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_STORE)                           \
+    if (epi == EPI_GELU_PRE) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_GELU_PRE)                     \
+    if (epi == EPI_F32) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_F32)                               \
+    HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_GENERIC)                                               \
+  }                                                                                                  \
+  if (!a.a_mn && a.b_mn) {                                                                           \
+    if (epi == EPI_STORE) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_STORE)                            \
+    if (epi == EPI_DGELU) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_DGELU)                            \
+    if (epi == EPI_ACCUM) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_ACCUM)                            \
+    HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_GENERIC)                                                \
+  }                                                                                                  \
+  if (a.a_mn && a.b_mn) {                                                                            \
+    if (epi == EPI_F32) HAMT_LAUNCH(BN_, true, true, PAIR_, EPI_F32)                                 \
+    HAMT_LAUNCH(BN_, true, true, PAIR_, EPI_GENERIC)                                                 \
+  }                                                                                                  \
+  HAMT_LAUNCH(BN_, true, false, PAIR_, EPI_GENERIC)
   if (pair) { HAMT_DISPATCH(256, true) }
   if (bn == 256) { HAMT_DISPATCH(256, false) }
   HAMT_DISPATCH(128, false)
+#undef HAMT_LAUNCH
 #undef HAMT_DISPATCH
 }
 

@@ -17,6 +17,7 @@ struct GemmArgs {
   float alpha;
   int tile_n;                               // 0 = auto, else 128 / 256
   int splits;                               // 0 = auto (only with out_mode 2)
+  float* colsum;                            // fp32 [N] or null: += column sums of the stored bf16 output (fused bias gradient)
 };
 int gemm_bf16(const GemmArgs& a, cudaStream_t st);
 void gemm_set_auto_pair(int on);

@@ -129,9 +129,10 @@ def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
     w1, w2 = inter.dense.weight, out_mod.dense.weight
     dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(out_mod.dense.bias), drop=d_hid, dres_out=dx_out)
     _wgrad(A, dt, a, w2)
-    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h)
+    b1 = inter.dense.bias
+    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h,
+                  colsum=A.grad(b1) if (b1 is not None and b1.requires_grad) else None)     # bias gradient fused into the dgrad epilogue
     _wgrad(A, dh, x, w1)
-    _bgrad(A, dh, inter.dense.bias)
     ops.gemm(dh, A.w16(w1), b_mn=True, out=dx, accumulate=True)
     return dx
 

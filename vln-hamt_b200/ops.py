@@ -52,8 +52,10 @@ def _check_bf16_2d(t: torch.Tensor, name: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, aux_mode: int = AUX_NONE, aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         out_dtype=BF16, accumulate: bool = False, alpha: float = 1.0, tile_n: int = 0, splits: int = 0) -> torch.Tensor:
-    """D[M,N] = act(alpha * sum_k A(m,k) B(n,k) + bias).  a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn)."""
+         out_dtype=BF16, accumulate: bool = False, alpha: float = 1.0, tile_n: int = 0, splits: int = 0,
+         colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[M,N] = act(alpha * sum_k A(m,k) B(n,k) + bias).  a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn).
+    colsum (fp32 [N]): += column sums of the stored bf16 D (fused bias gradient)."""
     _check_bf16_2d(a, "gemm.a")
     _check_bf16_2d(b, "gemm.b")
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
@@ -71,10 +73,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         raise ValueError("gemm: bias must be fp32 [N]")
     if aux_mode != AUX_NONE:
         _check_bf16_2d(aux, "gemm.aux")
+    if colsum is not None and (colsum.dtype != F32 or colsum.numel() != N or not colsum.is_contiguous()):
+        raise ValueError("gemm: colsum must be contiguous fp32 [N]")
     lib = _lib.load()
     rc = lib.hamt_gemm_bf16(a.data_ptr(), int(a_mn), a.stride(0), b.data_ptr(), int(b_mn), b.stride(0), out.data_ptr(), out.stride(0),
                             out_f32, (2 if out_f32 else 1) if accumulate else 0, M, N, K, _ptr(bias), act, aux_mode, _ptr(aux),
-                            aux.stride(0) if aux is not None else 0, alpha, tile_n, splits, _stream())
+                            aux.stride(0) if aux is not None else 0, alpha, tile_n, splits, _ptr(colsum), _stream())
     _lib.check(rc, "gemm_bf16")
     return out
 
