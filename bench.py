@@ -142,6 +142,9 @@ def main():
     ap.add_argument("--dp-mode", default="overlap", choices=["graph", "after", "overlap"],
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the device-resident timed region with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit after it; "
+                         "numbers printed in this mode are not bench values")
     ap.add_argument("--diag", action="store_true", help="print the e2e host-time breakdown and the per-signature GEMM table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -155,7 +158,7 @@ def main():
 
     import torch.distributed as dist
     import hamt_b200  # noqa: F401
-    from hamt_b200 import _lib, dp, graph, ops, synth
+    from hamt_b200 import _lib, dp, graph, loader, ops, synth
     from hamt_b200.config import HamtConfig
     from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
 
@@ -180,18 +183,16 @@ def main():
     host_batches, dev_batches = [], []
     for i, t in enumerate(schedule):
         b = synth.make_batch(t, batch_size=batch_size_of(t, B), seed=1000 * rank + i, **SHAPE)
-        hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        hb = dict(b)                                     # collated host batch; packed into pinned blobs by prefetch() in warm-up
         host_batches.append(hb)
         db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}
         if t in ("mlm", "mrc"):      # device-resident leg: the row indices are part of the resident batch
             db = graph.add_sync_free_extras(t, db)
             hb = graph.add_sync_free_extras(t, hb)
-            hb = {k: (v.pin_memory() if torch.is_tensor(v) and not v.is_pinned() else v) for k, v in hb.items()}
             host_batches[-1] = hb
         if t == "itm":
             db["_hist_masks_host"] = b["hist_masks"]
         dev_batches.append(db)
-    h2d_bytes = float(np.mean([sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches]))
 
     use_graphs = not args.no_graphs
 
@@ -232,39 +233,23 @@ def main():
 
     copy_stream = torch.cuda.Stream(device=dev)
 
-    staging = [None] * len(schedule)     # persistent device staging buffers, one set per schedule slot (no allocation in the loop)
+    packed = [None] * len(schedule)      # one PackedBatch (pinned host blob + device blob) per schedule slot, built in warm-up
 
     def prefetch(i):
         """Host -> device copy of step i's batch from pinned memory on a side stream, like the reference's PrefetchLoader
-        (pretrain_src/data/loader.py:90-125): the copy of batch i+1 overlaps the compute of batch i."""
+        (pretrain_src/data/loader.py:90-125): the copy of batch i+1 overlaps the compute of batch i.  One cudaMemcpyAsync of
+        the packed blob (hamt_b200.loader); the ITM negative plan is drawn on the host (reference RNG order) into the blob."""
         j = i % len(schedule)
         task = schedule[j]
-        np.random.seed(i); torch.manual_seed(i)
-        hb = graph.add_sync_free_extras(task, host_batches[j]) if (use_graphs and task == "itm") else host_batches[j]
-        if staging[j] is None:
-            st = {}
-            for k, v in hb.items():
-                if torch.is_tensor(v):
-                    st[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
-                elif k == "itm_plan" and v is not None:
-                    st[k] = (None if v[0] is None else torch.empty(v[0].shape, dtype=v[0].dtype, device=dev),
-                             [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in v[1]])
-                else:
-                    st[k] = v
-            staging[j] = st
-        db = staging[j]
-        with torch.cuda.stream(copy_stream):
-            for k, v in hb.items():
-                if torch.is_tensor(v):
-                    db[k].copy_(v, non_blocking=True)
-                elif k == "itm_plan" and v is not None:
-                    if v[0] is not None:
-                        db[k][0].copy_(v[0], non_blocking=True)
-                    for dst, src in zip(db[k][1], v[1]):
-                        dst.copy_(src, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return db, ev
+        if packed[j] is None:
+            np.random.seed(i); torch.manual_seed(i)
+            hb = graph.add_sync_free_extras(task, host_batches[j]) if use_graphs else host_batches[j]
+            packed[j] = loader.PackedBatch(hb, dev)
+        elif use_graphs and task == "itm":
+            np.random.seed(i); torch.manual_seed(i)
+            packed[j].fill(graph.add_sync_free_extras(task, host_batches[j]), only_plan=True)
+        db = packed[j].to_device(copy_stream)
+        return db, packed[j].ready
 
     diag_t = {"prefetch": 0.0, "step": 0.0, "item": 0.0}
 
@@ -278,29 +263,30 @@ def main():
         samples, d2h = 0, 0
         DEPTH = 2                                           # batches in flight ahead of the compute (absorbs PCIe / host jitter)
         queue = [prefetch(k) for k in range(min(DEPTH, n_steps))] if from_host else None
-        prev = None
+        reader = loader.LossReader(depth=4)
         for i in range(n_steps):
             j = i % len(schedule)
             if from_host:
                 t0 = time.perf_counter()
                 batch, ev = queue.pop(0)
                 if i + DEPTH < n_steps:
-                    queue.append(prefetch(i + DEPTH) if copy else (staging[(i + DEPTH) % len(schedule)], ev))
+                    queue.append(prefetch(i + DEPTH) if copy else (packed[(i + DEPTH) % len(schedule)].dev_views, ev))
                 torch.cuda.current_stream().wait_event(ev)
                 t1 = time.perf_counter()
                 lm = step(i, batch).float().mean()         # tiny reduction enqueued behind the step
                 t2 = time.perf_counter()
-                if prev is not None and read_loss:         # device -> host read of the previous step's result while this one runs
-                    assert np.isfinite(prev.item())
-                    d2h += 4
-                prev = lm
+                if read_loss:
+                    reader.push(lm)                        # async device -> host copy of this step's result + event
+                    if reader.pending() > 1:               # read the PREVIOUS step's loss while this step runs
+                        assert np.isfinite(reader.pop())
+                        d2h += 4
                 t3 = time.perf_counter()
                 diag_t["prefetch"] += t1 - t0; diag_t["step"] += t2 - t1; diag_t["item"] += t3 - t2
             else:
                 step(i, dev_batches[j])
             samples += batch_size_of(schedule[j], B)
-        if prev is not None:
-            assert np.isfinite(prev.item())
+        while from_host and reader.pending():
+            assert np.isfinite(reader.pop())
             d2h += 4
         e1.record()
         sync_all()
@@ -314,13 +300,23 @@ def main():
 
     for i in range(max(args.warmup, len(schedule) if use_graphs else 0)):      # every (task, signature) graph is captured in warm-up
         step(i, dev_batches[i % len(schedule)])
-    if use_graphs:
-        for i in range(len(schedule)):
-            step(i, host_batches[i])
+    for i in range(len(schedule)):                       # build the packed slots + run every step once from the host path
+        db, ev = prefetch(i)
+        torch.cuda.current_stream().wait_event(ev)
+        step(i, db)
     graph_launches.clear()
+    h2d_bytes = float(np.mean([pb.layout.payload_bytes for pb in packed]))     # bytes of the tensors copied per step (padding excluded)
     sampler = ClockSampler(local_rank)
     sampler.start()
     n_graphs0 = len(trainer.steps) if trainer else 0
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ms, samples, launches, _ = timed(args.steps, from_host=False)
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_range": True, "steps": args.steps, "launches": int(launches), "note": "run under a profiler: not a bench value"}), flush=True)
+        os._exit(0)
     ms, samples, launches, _ = timed(args.steps, from_host=False)
     clocks = sampler.result()
     ms_e2e, samples_e2e, _, d2h = timed(args.steps, from_host=True)
@@ -424,7 +420,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h / args.steps),
                     "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_only_ms_per_step": round(h2d_ms, 3),
                     "graphs_captured_in_timed_regions": n_graphs1 - n_graphs0,
-                    "how": "pinned host batch -> device on a copy stream one step ahead (PrefetchLoader style) -> captured step -> loss read back"},
+                    "how": "packed pinned host batch -> one cudaMemcpyAsync on a copy stream, 2 batches ahead (PrefetchLoader style, hamt_b200.loader) -> captured step -> per-step loss through a pinned slot + event (read one step behind)"},
             "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": round(achieved_tf, 1), "peak": peaks["tf_sustained"],
                          "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf_sustained"], 3), "traffic": traffic, "peak_source": peaks["src"] + " (sustained)",
                          "launches": n_gemm, "share_of_step": round(gemm_ms / n_prof / (ms / args.steps), 3),

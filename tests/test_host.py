@@ -133,3 +133,31 @@ def _dp_worker(rank, world, port, overlap):
 @pytest.mark.parametrize("overlap", [False, True])
 def test_data_parallel_grad_exchange_gloo_world2(overlap):
     mp.spawn(_dp_worker, args=(2, _free_port(), overlap), nprocs=2, join=True)
+
+
+def test_packed_batch_layout_roundtrip_on_cpu():
+    """loader.Layout: every tensor of a collated batch (incl. the ITM negative plan) gets an aligned slot of one blob and the
+    views reproduce the batch exactly (the transport the e2e path uses; reference: PrefetchLoader / move_to_cuda,
+    pretrain_src/data/loader.py:90-125)."""
+    import numpy as np
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import graph, loader, synth
+    for task in ("mlm", "sap", "mrc", "itm"):
+        b = synth.make_batch(task, batch_size=4, txt_len=20, hist_len=3, seed=7, ragged=True)
+        np.random.seed(0); torch.manual_seed(0)
+        b = graph.add_sync_free_extras(task, b)
+        lay = loader.Layout(b)
+        assert all(off % 256 == 0 for _, off, _, _, _ in lay.entries)
+        blob = torch.zeros(lay.nbytes, dtype=torch.uint8)
+        views = lay.views(blob)
+        for (pa, va), (pb, vb) in zip(loader.flatten(views), loader.flatten(b)):
+            assert pa == pb and va.dtype == vb.dtype and va.shape == vb.shape
+            va.copy_(vb)
+        again = lay.views(blob)
+        for (pa, va), (pb, vb) in zip(loader.flatten(again), loader.flatten(b)):
+            assert torch.equal(va, vb), pa
+        assert set(k for k in b if not k.startswith("_")) == set(again)
+        for k, v in b.items():
+            if v is None:
+                assert again[k] is None
+        assert graph._signature(task, again) == graph._signature(task, b)

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .loader import Layout, flatten
 from .vilmodel import itm_negative_plan
 
 _INDEX_KEYS = {"mlm": ("txt_label_rows", "txt_labels", -1), "mrc": ("hist_mrc_rows", "hist_mrc_masks", None)}
@@ -76,16 +77,13 @@ class GraphedStep:
     def __init__(self, model, task: str, batch: Dict, post_backward=None, warmup: int = 2):
         self.model, self.task = model, task
         dev = next(model.parameters()).device
-        self.static = {}
-        for k, v in batch.items():
-            if k.startswith("_"):
-                continue
-            if torch.is_tensor(v):
-                self.static[k] = v.to(dev).clone()
-            elif k == "itm_plan" and v is not None:
-                self.static[k] = (None if v[0] is None else v[0].to(dev).clone(), [t.to(dev).clone() for t in v[1]])
-            else:
-                self.static[k] = v
+        # static inputs of the captured step: one packed device blob (loader.Layout), so a packed batch arrives with ONE copy
+        self.layout = Layout(batch)
+        self.blob = torch.empty(self.layout.nbytes, dtype=torch.uint8, device=dev)
+        self.static = self.layout.views(self.blob)
+        self._static_flat = dict(flatten(self.static))
+        for path, t in flatten(batch):
+            self._static_flat[path].copy_(t)
         self.signature = _signature(task, batch)
 
         def body():
@@ -121,17 +119,12 @@ class GraphedStep:
         return _signature(task, batch) == self.signature
 
     def __call__(self, batch: Dict) -> torch.Tensor:
-        for k, v in batch.items():
-            if k.startswith("_"):
-                continue
-            s = self.static.get(k)
-            if torch.is_tensor(v):
-                s.copy_(v, non_blocking=True)
-            elif k == "itm_plan" and v is not None:
-                if v[0] is not None:
-                    s[0].copy_(v[0], non_blocking=True)
-                for dst, src in zip(s[1], v[1]):
-                    dst.copy_(src, non_blocking=True)
+        packed = batch.get("_packed")
+        if packed is not None and packed.layout.key == self.layout.key:
+            self.blob.copy_(packed.dev, non_blocking=True)           # one device-to-device copy of the whole batch
+        else:
+            for path, t in flatten(batch):
+                self._static_flat[path].copy_(t, non_blocking=True)
         self.graph.replay()
         arena = self.model.arena()
         # restore the host-side gradient bookkeeping of this task (graphs of other tasks may have run in between)
