@@ -111,11 +111,54 @@ def cpu_reference_samples_per_sec(steps, warmup, batch, threads=None, tasks=None
     return n / dt, dt, threads
 
 
+def gpu_eager_port_samples_per_sec(batch=64, steps=12, warmup=12, autocast=True):
+    """Informational third column of SURVEY 8(d): the same oracle port run as plain torch eager ON THE GPU (train mode without
+    dropout masks, fwd + bwd, CUDA events) -- what 'reference GPU torch eager, 1 x B200' costs on this box.  The unmodified reference
+    cannot travel to the GPU box (it lives outside the repo), the port issues the same aten ops per layer."""
+    from oracle import hamt_oracle as O
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    dev = torch.device("cuda", 0)
+    cfg = HamtConfig()
+    model = MultiStepNavCMTPreTraining(cfg)
+    sd = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in synth.seeded_state_dict(model, seed=0).items()}
+    sd["mlm_head.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
+    del model
+    batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_batch(t, batch_size=batch_size_of(t, batch), seed=i, **SHAPE).items()}
+               for i, t in enumerate(SCHEDULE)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize(); e0.record(); n = 0
+        t = SCHEDULE[i % len(SCHEDULE)]
+        np.random.seed(i); torch.manual_seed(i)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            loss = O.pretrain_forward(sd, cfg, batches[i % len(SCHEDULE)], t, compute_loss=True)
+        loss.float().mean().backward()
+        for v in sd.values():
+            v.grad = None
+        n += batch_size_of(t, batch)
+    e1.record(); torch.cuda.synchronize()
+    return n / (e0.elapsed_time(e1) * 1e-3)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     batch = args.ref_batch
     sps, dt, threads = cpu_reference_samples_per_sec(args.steps, args.warmup, batch)
+    gpu_eager = None
+    if torch.cuda.is_available() and not args.no_gpu_eager:
+        gpu_eager = {"what": "oracle port as torch eager on 1 GPU, batch 64, 6-task schedule, fwd+bwd, CUDA events (informational; not the reference arm's value)"}
+        for name, ac in (("bf16_autocast", True), ("fp32", False)):
+            try:
+                gpu_eager[name + "_samples_per_s"] = round(gpu_eager_port_samples_per_sec(autocast=ac), 1)
+            except Exception as e:  # noqa: BLE001
+                gpu_eager[name + "_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+            torch.cuda.empty_cache()
     line = {"impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -124,6 +167,8 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} steps of the 6-task schedule at batch {batch}, fp32 torch CPU autograd of oracle/hamt_oracle.py"},
             "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if gpu_eager is not None:
+        line["gpu_eager_port"] = gpu_eager
     print(json.dumps(line), flush=True)
 
 
@@ -138,6 +183,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--tasks", default=None, help="comma list overriding the 6-task schedule (e.g. sap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="--impl reference: skip the informational torch-eager-on-GPU timing of the oracle port")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--dp-mode", default="overlap", choices=["graph", "after", "overlap"],
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")

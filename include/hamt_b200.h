@@ -119,6 +119,16 @@ int hamt_ce_bwd(const float* logits, long long ld, const long long* labels, cons
 int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);   /* out[i] = x[idx[i]] */
 int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);  /* out[idx[i]] = x[i] */
 
+/* fused optimizer step over the flat parameter arena: HF-style AdamW exactly as pretrain_src/optim/adamw.py:53-110
+ * (bias correction, eps outside the sqrt, decoupled decay AFTER the update with lr * wd; parameters without a gradient this step are
+ * skipped and keep their step counter, :64-66) + torch.nn.utils.clip_grad_norm_ (main_r2r.py:271-274) + bf16 shadow refresh + gradient
+ * zeroing (optimizer.zero_grad(), main_r2r.py:281).  Segment s = one parameter; chunk_seg maps every 64-element chunk of the flat
+ * buffers to its segment (-1 = alignment padding).  workspace[0] = global gradient norm (before clipping), [1] = clip coefficient. */
+int hamt_adamw_workspace_floats(void);
+int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, int nseg,
+                    const unsigned char* seg_active, const float* seg_wd, int* seg_step, float* seg_step_size, const float* lr, double beta1,
+                    double beta2, double eps, int correct_bias, float max_grad_norm, int want_norm, int zero_grad, float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,7 +278,7 @@ def pano_encode(sd: State, prefix: str, pano_img: Tensor, pano_ang: Tensor, n_la
     if drop_pano_emb:
         e = _hidden_drop(e, dp)
     e = rg.q(e)
-    zero_mask = torch.zeros(N, 1, 1, P)
+    zero_mask = torch.zeros(N, 1, 1, P, device=e.device)
     for l in range(n_layers):
         e = bert_layer(sd, f"{prefix}.pano_encoder.layer.{l}", e, zero_mask, n_heads, rg, dp)
     return e.mean(dim=1)
@@ -346,7 +346,7 @@ def backbone(sd: State, cfg, txt_ids, txt_masks, hist_img, hist_ang, hist_pano_i
     txt_mask = ext_mask(txt_masks)
     txt = text_embeddings(sd, prefix + ".embeddings", txt_ids, rg, dp)
     hist_mask = ext_mask(hist_masks)
-    pos_ids = torch.arange(hist_img.shape[1])[None] if hist_img is not None else None
+    pos_ids = torch.arange(hist_img.shape[1], device=hist_img.device)[None] if hist_img is not None else None
     cls, vp = history_embeddings(sd, cfg, prefix + ".hist_embeddings", hist_img, hist_ang, hist_pano_img,
                                  hist_pano_ang, pos_ids, B, rg, dp)
     hist = cls if vp is None else torch.cat([cls, vp], 1)
@@ -403,7 +403,7 @@ def backbone_itm(sd: State, cfg, txt_ids, txt_masks, hist_img, hist_ang, hist_pa
     pos_w = sd[hp + ".position_embeddings.weight"]
 
     def with_pos(pos_ids):
-        return rg.q(_hidden_drop(layer_norm(sd, hp + ".layer_norm", vp_nopos + pos_w[pos_ids]), dp))
+        return rg.q(_hidden_drop(layer_norm(sd, hp + ".layer_norm", vp_nopos + pos_w[pos_ids.to(pos_w.device)]), dp))
 
     def h_layers(x):
         for l in range(cfg.num_h_layers):
@@ -412,8 +412,10 @@ def backbone_itm(sd: State, cfg, txt_ids, txt_masks, hist_img, hist_ang, hist_pa
 
     hist = h_layers(torch.cat([cls, with_pos(torch.arange(T)[None])], 1))
     if plan is None:
-        plan = itm_negative_plan(B, hist_masks, T, num_neg_trajs)
+        plan = itm_negative_plan(B, hist_masks.cpu(), T, num_neg_trajs)
     neg_idxs, shuffled = plan
+    if neg_idxs is not None:
+        neg_idxs = neg_idxs.to(hist.device)
     neg_embeds, neg_masks = [], []
     if neg_idxs is not None:
         for k in range(neg_idxs.shape[1]):
@@ -510,7 +512,7 @@ def pretrain_forward(sd: State, cfg, batch: dict, task: str, compute_loss: bool 
     if task.startswith("itm"):
         fused = backbone_itm(sd, cfg, g("txt_ids"), g("txt_masks"), *hist_args, 4, rg=rg, dp=dp, plan=itm_plan)
         scores = mlp_head(sd, "itm_head", fused, rg, dp, False).squeeze(2)
-        tgt = torch.zeros(fused.shape[0], dtype=torch.long)
+        tgt = torch.zeros(fused.shape[0], dtype=torch.long, device=fused.device)
         if compute_loss:
             return F.cross_entropy(scores, tgt, reduction="none")
         return scores, tgt

@@ -28,7 +28,9 @@ def _ref(q, k, v, mask, B, Sq, Sk):
 
 
 @pytest.mark.parametrize("B,Sq,Sk,masked", [(3, 36, 36, False), (4, 80, 80, True), (4, 80, 53, True), (4, 53, 80, True), (2, 16, 5, True),
-                                             (2, 1, 17, True), (2, 128, 128, True), (5, 17, 100, True)])
+                                             (2, 1, 17, True), (2, 128, 128, True), (5, 17, 100, True),
+                                             # long sequences (RxR instructions, BASELINE config 4: L = 300, 58 vision tokens): recompute backward
+                                             (2, 300, 300, True), (2, 300, 58, True), (2, 58, 300, True), (1, 129, 40, False), (1, 250, 512, True)])
 def test_attention_fwd_bwd(B, Sq, Sk, masked):
     ops = _ops()
     g = torch.Generator().manual_seed(B * 1000 + Sq * 10 + Sk)

@@ -265,3 +265,61 @@ def test_finetune_navcmt_modes_vs_reference_golden():
         for got, want in zip(vis[1:], rec["visual"][1:]):
             assert _err(got, want) < HID
         assert torch.equal(vis[0].float().cpu().argmax(1), rec["visual"][0].argmax(1))
+
+
+STRESS = {
+    # BASELINE config 4 (RxR): text_len 300, multilingual-sized position table, 512-d features, hist 20 x 36; the XLM-R vocabulary is
+    # cut to 6000 rows so that the CPU oracle stays fast (the embedding gather / tied decoder are size-agnostic)
+    "rxr": (dict(image_feat_size=512, max_position_embeddings=514, vocab_size=6000, num_l_layers=2, num_x_layers=2, num_h_pano_layers=1),
+            dict(batch_size=2, txt_len=300, hist_len=20, feat=512, vocab_hi=6000)),
+    # BASELINE config 5 (R4R): hist_len 40 x 36 views (41 + 37 = 78 vision tokens)
+    "r4r": (dict(num_l_layers=1, num_x_layers=2, num_h_pano_layers=2), dict(batch_size=2, txt_len=80, hist_len=40)),
+}
+
+
+@pytest.mark.parametrize("name", ["rxr", "r4r"])
+def test_stress_configs_forward_and_gradients_vs_oracle(name):
+    """BASELINE configs 4 and 5 as parity cases: eval logits (SAP, MLM) against the fp32 oracle, then train-mode (dropout 0)
+    parameter gradients of a projected SAP output against autograd through the bf16-regime oracle.  RxR exercises the
+    long-sequence attention backward (S = 300 > 128)."""
+    from hamt_b200 import synth
+    from oracle import hamt_oracle as O
+    cfg_over, bkw = STRESS[name]
+    cfg, model, sd = _build(cfg_over, 11)
+    model.eval()
+    for task in ("sap", "mlm"):
+        b = synth.make_batch(task, seed=21, ragged=True, **bkw)
+        with torch.no_grad():
+            out = model(_to_dev(b), task, compute_loss=False)
+            ref = O.pretrain_forward(sd, cfg, b, task, compute_loss=False)
+        assert _err(out, ref) < TOL_LOGITS, (name, task, _err(out, ref))
+        if task == "sap":
+            top2 = ref.topk(2, dim=1).values
+            ok = (top2[:, 0] - top2[:, 1]) > 2 * TOL_LOGITS
+            assert torch.equal(out.float().cpu().argmax(1)[ok], ref.argmax(1)[ok])
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    b = synth.make_batch("sap", seed=22, ragged=True, **bkw)
+    loss = _proj_loss(model(_to_dev(b), "sap", compute_loss=False), 100)
+    loss.backward()
+    torch.cuda.synchronize()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    sdr["mlm_head.predictions.decoder.weight"] = sdr["bert.embeddings.word_embeddings.weight"]
+    ref = _proj_loss(O.pretrain_forward(sdr, cfg, b, "sap", compute_loss=False, rg=O.BF16), 100)
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-2 * max(1.0, abs(float(ref.detach())))
+    ref.backward()
+    bad, checked = [], 0
+    for k, p in model.named_parameters():
+        g_ref = sdr[k].grad
+        if g_ref is None or g_ref.abs().max().item() == 0:
+            continue
+        assert p.grad is not None, f"{k}: missing gradient"
+        floor = 1e-3 * (g_ref.numel() ** 0.5)
+        rel = (p.grad.float().cpu() - g_ref).norm().item() / max(g_ref.norm().item(), floor)
+        checked += 1
+        if rel > 0.10:
+            bad.append((k, round(rel, 4)))
+    assert checked > 20
+    assert not bad, f"{name}: gradient mismatch ({len(bad)} of {checked}): {sorted(bad, key=lambda t: -t[1])[:8]}"

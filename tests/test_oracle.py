@@ -2,6 +2,7 @@
 reference (tests/golden/*.pt, oracle/make_golden.py), and -- where the reference checkout exists -- the reference run live.
 Also documents, by measurement, why a bf16 pipeline of this depth cannot meet a 1e-3 max-abs bar on logits."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -138,3 +139,51 @@ def test_bf16_regime_rounding_chaos():
     assert d32 < 2e-4
     assert d16 > 1e-3, "bf16 regime turned out to be stable -- tighten the model-level tolerance"
     assert gap < 4e-2
+
+
+def _run_optim_oracle():
+    from oracle import optim_oracle as OO
+    from oracle import make_golden_optim as G
+    params, grads = G.scenario()
+    ps = [p.clone() for p in params]
+    st = OO.AdamWState(ps, G.WD, betas=(0.9, 0.98))
+    norms, traj = [], []
+    for t in range(G.STEPS):
+        lr = G.LR0 * OO.warmup_linear(t + 1, G.WARMUP, G.TOTAL)
+        lr = lr if lr > 0 else 1e-8
+        gs = [None if g is None else g.clone() for g in grads[t]]
+        norms.append(OO.clip_grad_norm(gs, G.MAX_NORM))
+        st.step(gs, lr)
+        traj.append([p.clone() for p in ps])
+    return st, norms, traj
+
+
+def test_optim_oracle_matches_reference_golden():
+    """oracle/optim_oracle.py against the trajectory the UNMODIFIED reference AdamW + clip_grad_norm_ + warmup_linear produced
+    (tests/golden/adamw_reference.pt, oracle/make_golden_optim.py): bit-exact on CPU, including per-parameter step counters of
+    parameters that were skipped in some steps."""
+    rec = torch.load(os.path.join(GOLD, "adamw_reference.pt"))
+    st, norms, traj = _run_optim_oracle()
+    assert norms == pytest.approx(rec["norms"], rel=1e-6)
+    assert any(n > 5.0 for n in norms) and any(n < 5.0 for n in norms), "the scenario must cover clipped and unclipped steps"
+    for t, (a, b) in enumerate(zip(traj, rec["params"])):
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert torch.equal(x, y), (t, i, (x - y).abs().max())
+    assert [st.state[i]["step"] for i in range(len(traj[0]))] == rec["steps"]
+    assert len(set(rec["steps"])) > 1
+    for i in range(len(traj[0])):
+        assert torch.equal(st.state[i]["exp_avg"], rec["exp_avg"][i]) and torch.equal(st.state[i]["exp_avg_sq"], rec["exp_avg_sq"][i])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pretrain_src/optim"), reason="reference checkout not present on this machine")
+def test_optim_oracle_matches_live_reference_schedule():
+    sys.path.insert(0, "/root/reference/pretrain_src")
+    try:
+        from optim.sched import warmup_linear as ref_wl
+    finally:
+        sys.path.pop(0)
+    from oracle import optim_oracle as OO
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import optim as ours
+    for step in range(0, 30):
+        assert OO.warmup_linear(step, 5, 20) == ref_wl(step, 5, 20) == ours.warmup_linear(step, 5, 20)

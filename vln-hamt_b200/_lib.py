@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libhamt_b200.so")
 
 _lib = None
 
-vp, ll, i32, u32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_uint, C.c_float
+vp, ll, i32, u32, f32, f64 = C.c_void_p, C.c_longlong, C.c_int, C.c_uint, C.c_float, C.c_double
 
 
 class EmbedFeatDesc(C.Structure):
@@ -54,6 +54,8 @@ SIGNATURES = {
     "hamt_mean_pool_bwd": [vp, vp, i32, i32, i32, vp],
     "hamt_add_bf16": [vp, vp, vp, ll, vp],
     "hamt_mul_rows_bf16": [vp, vp, vp, i32, i32, i32, vp],
+    "hamt_adamw_workspace_floats": [],
+    "hamt_adamw_step": [vp, vp, vp, vp, vp, ll, vp, i32, vp, vp, vp, vp, vp, f64, f64, f64, i32, f32, i32, i32, vp, vp],
     "hamt_rowdot_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
     "hamt_rowdot_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "hamt_ce_fwd": [vp, ll, vp, vp, vp, i32, i32, vp],

@@ -37,6 +37,7 @@ class ParamArena:
         self.offsets: Dict[int, int] = {}
         self.params: List[nn.Parameter] = []
         self._shadow_version = None
+        self._fresh_version = None
         self._touched: List[nn.Parameter] = []
         self._sentinel: Optional[nn.Parameter] = None
         self.anchor = None
@@ -107,10 +108,13 @@ class ParamArena:
         # bf16 shadow refresh: ONE cast launch for every GEMM operand.  Training: every step (weights move every
         # optimizer step; in-place updates through `.data` bump no version counter, so this is unconditional --
         # 1 GB of traffic, ~0.2 ms).  Eval: only when a parameter's version counter moved or after training.
-        ver = None if training else sum(p._version for p in self.params)
-        if training or ver != self._shadow_version:
+        ver = sum(p._version for p in self.params) if (not training or self._fresh_version is not None) else None
+        if training and self._fresh_version is not None and ver == self._fresh_version:
+            pass        # the fused optimizer wrote the shadow together with the weights (optim.AdamW.step) and nothing changed since
+        elif training or ver != self._shadow_version:
             ops.cast_bf16(self.flat_param, out=self.flat_bf16)
-            self._shadow_version = ver
+            self._shadow_version = None if training else ver
+        self._fresh_version = None
         if training and self._sentinel is not None and self._sentinel.grad is None:
             # the caller cleared the gradients (zero_grad(set_to_none=True)): start a fresh accumulation
             self.flat_grad.zero_()
@@ -121,6 +125,20 @@ class ParamArena:
     def mark_dirty(self):
         """Parameters were modified without bumping flat_param's version counter (e.g. through .data)."""
         self._shadow_version = None
+        self._fresh_version = None
+
+    def shadow_is_fresh(self):
+        """Called by the fused optimizer: the bf16 shadow was written in the same pass as the fp32 weights, so the next training
+        step may skip its cast launch -- unless a parameter's version counter moves in between (load_state_dict, manual edits)."""
+        self._fresh_version = sum(p._version for p in self.params)
+        self._shadow_version = None
+
+    def grads_are_zero(self):
+        """Called by the fused optimizer after it zeroed the gradients of every touched parameter in its update pass: the next
+        step starts a fresh accumulation without the flat memset."""
+        for p in self._touched:
+            p.grad = None
+        self._touched, self._sentinel = [], None
 
     # ---------------------------------------------------------------- views
     def w16(self, p: nn.Parameter) -> torch.Tensor:

@@ -118,4 +118,13 @@ int hamt_mul_rows_bf16(const void* a, const void* v, void* out, int B, int S, in
   return mul_rows_bf16(a, v, out, B, S, H, (cudaStream_t)stream);
 }
 
+int hamt_adamw_workspace_floats(void) { return adamw_workspace_floats(); }
+int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, int nseg,
+                    const unsigned char* seg_active, const float* seg_wd, int* seg_step, float* seg_step_size, const float* lr, double beta1,
+                    double beta2, double eps, int correct_bias, float max_grad_norm, int want_norm, int zero_grad, float* workspace, void* stream) {
+  AdamWArgs a{param, grad, exp_avg, exp_avg_sq, shadow_bf16, total, chunk_seg, nseg, seg_active, seg_wd, seg_step, seg_step_size, lr,
+              beta1, beta2, eps, correct_bias, max_grad_norm, want_norm, zero_grad, workspace};
+  return adamw_step(a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
 // backward.  Phase 1: warp w owns keys [16w,16w+16): dK, dV in registers, dS^T -> smem.
 //            Phase 2: warp w owns 16 queries: dQ = dS K.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
+// LONG = false: Sq, Sk <= 128 (every R2R / R4R shape): dS goes through shared memory for the dQ pass, two CTAs per SM.
+// LONG = true : long sequences (RxR instructions, L = 300): Q, dO, K, V of the (batch, head) pair fill shared memory, so the dQ
+//               pass RECOMPUTES S and dP from registers (7 instead of 5 small matmuls) and needs no dS buffer; one CTA per SM.
+template <bool LONG>
+__global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP p) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 15) & ~15;
@@ -198,8 +202,8 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
   __nv_bfloat16* sDO = sQ + Sq_pad * LDS;
   __nv_bfloat16* sK = sDO + Sq_pad * LDS;
   __nv_bfloat16* sV = sK + Sk_pad * LDS;
-  __nv_bfloat16* sDS = sV + Sk_pad * LDS;           // [Sq_pad][LDP]
-  float* sMask = reinterpret_cast<float*>(sDS + Sq_pad * LDP);
+  __nv_bfloat16* sDS = sV + Sk_pad * LDS;           // [Sq_pad][LDP]  (absent when LONG)
+  float* sMask = reinterpret_cast<float*>(sDS + (LONG ? 0 : Sq_pad * LDP));
   float* sLse = sMask + Sk_pad;
   float* sDelta = sLse + Sq_pad;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -211,22 +215,31 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // delta_i = sum_d dO[i,d] * O[i,d]  (O = saved forward output).  Item = (row, 16-byte chunk): the O chunks are requested
   // from global memory while the cp.async staging is still in flight; at most 4 items per thread (blockDim >= Sq_pad * 2).
-  uint4 o_reg[4];
+  constexpr int kItems = LONG ? 1 : 4;
+  uint4 o_reg[kItems];
+  if (!LONG) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int item = threadIdx.x + k * blockDim.x, r = item >> 3, c = (item & 7) * 8;
-    o_reg[k] = make_uint4(0, 0, 0, 0);
-    if (item < Sq_pad * 8 && r < p.Sq) o_reg[k] = *reinterpret_cast<const uint4*>(p.out + b * p.o_bs + (long long)r * p.ldo + h * D + c);
+    for (int k = 0; k < kItems; ++k) {
+      const int item = threadIdx.x + k * blockDim.x, r = item >> 3, c = (item & 7) * 8;
+      o_reg[k] = make_uint4(0, 0, 0, 0);
+      if (item < Sq_pad * 8 && r < p.Sq) o_reg[k] = *reinterpret_cast<const uint4*>(p.out + b * p.o_bs + (long long)r * p.ldo + h * D + c);
+    }
   }
   for (int i = threadIdx.x; i < Sq_pad; i += blockDim.x) sLse[i] = i < p.Sq ? p.lse[((long long)b * p.heads + h) * p.Sq + i] : 0.f;
   stage_wait();
   __syncthreads();
+  const int n_iter = LONG ? (Sq_pad * 8 + (int)blockDim.x - 1) / (int)blockDim.x : kItems;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < n_iter; ++k) {
     const int item = threadIdx.x + k * blockDim.x, r = item >> 3, c = (item & 7) * 8;
     if (item < Sq_pad * 8) {                     // whole warps are in or out (Sq_pad * 8 and blockDim are multiples of 32)
+      if (LONG) {
+        o_reg[0] = make_uint4(0, 0, 0, 0);
+        if (r < p.Sq) o_reg[0] = *reinterpret_cast<const uint4*>(p.out + b * p.o_bs + (long long)r * p.ldo + h * D + c);
+      }
+      const uint4 o4 = o_reg[LONG ? 0 : k];
       const uint4 d4 = *reinterpret_cast<const uint4*>(sDO + r * LDS + c);
-      const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, ow[4] = {o_reg[k].x, o_reg[k].y, o_reg[k].z, o_reg[k].w};
+      const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
       float acc = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
           }
           pd[nt][e] = pe * mult;
           dsv[nt][e] = pe * (dpt[nt][e] * mult - sDelta[qi]) * p.scale;
-          sDS[qi * LDP + key] = __float2bfloat16_rn(dsv[nt][e]);
+          if (!LONG) sDS[qi * LDP + key] = __float2bfloat16_rn(dsv[nt][e]);
         }
       uint32_t ap[4], as_[4];
       ap[0] = pack_bf16(pd[0][0], pd[0][1]); ap[1] = pack_bf16(pd[0][2], pd[0][3]);
@@ -326,15 +339,68 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const AttnP p) {
     float dq[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    for (int kk = 0; kk < Sk_pad / 16; ++kk) {
-      uint32_t a[4];
-      ldsm_x4(a, sDS_a + 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDP + kk * 16 + 8 * (lane >> 4)));
+    if (!LONG) {
+      for (int kk = 0; kk < Sk_pad / 16; ++kk) {
+        uint32_t a[4];
+        ldsm_x4(a, sDS_a + 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDP + kk * 16 + 8 * (lane >> 4)));
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t bk[4];
-        ldsm_x4_t(bk, sK_a + 2u * ((kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4)));
-        mma16816(dq[2 * dp], a, bk[0], bk[1]);
-        mma16816(dq[2 * dp + 1], a, bk[2], bk[3]);
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bk[4];
+          ldsm_x4_t(bk, sK_a + 2u * ((kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4)));
+          mma16816(dq[2 * dp], a, bk[0], bk[1]);
+          mma16816(dq[2 * dp + 1], a, bk[2], bk[3]);
+        }
+      }
+    } else {
+      // recompute S = Q K^T and dP = dO V^T for this warp's 16 queries, 16 keys at a time (operand layouts as in the forward)
+      uint32_t aq[4][4], ad[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t off = 2u * ((qb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + ks * 16 + 8 * (lane >> 4));
+        ldsm_x4(aq[ks], sQ_a + off);
+        ldsm_x4(ad[ks], sDO_a + off);
+      }
+      const int row0 = qb * 16 + g;       // rows row0, row0 + 8
+      const float lse_r[2] = {sLse[row0], sLse[row0 + 8]}, del_r[2] = {sDelta[row0], sDelta[row0 + 8]};
+      for (int kg = 0; kg < Sk_pad / 16; ++kg) {
+        float sc[2][4], dp_[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = dp_[i][0] = dp_[i][1] = dp_[i][2] = dp_[i][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t bk[4], bv[4];
+          const uint32_t off = 2u * ((kg * 16 + (lane & 7) + 8 * (lane >> 4)) * LDS + ks * 16 + 8 * ((lane >> 3) & 1));
+          ldsm_x4(bk, sK_a + off);
+          ldsm_x4(bv, sV_a + off);
+          mma16816(sc[0], aq[ks], bk[0], bk[1]);
+          mma16816(sc[1], aq[ks], bk[2], bk[3]);
+          mma16816(dp_[0], ad[ks], bv[0], bv[1]);
+          mma16816(dp_[1], ad[ks], bv[2], bv[3]);
+        }
+        float dsv[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kg * 16 + nt * 8 + 2 * t + (e & 1);
+            const int qi = row0 + 8 * (e >> 1);
+            float pe = 0.f, mult = 1.f;
+            if (key < p.Sk && qi < p.Sq) {
+              pe = __expf(sc[nt][e] * p.scale + sMask[key] - lse_r[e >> 1]);
+              if (ds.on) mult = drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + qi) * p.Sk + key);
+            }
+            dsv[nt][e] = pe * (dp_[nt][e] * mult - del_r[e >> 1]) * p.scale;
+          }
+        uint32_t a[4];
+        a[0] = pack_bf16(dsv[0][0], dsv[0][1]); a[1] = pack_bf16(dsv[0][2], dsv[0][3]);
+        a[2] = pack_bf16(dsv[1][0], dsv[1][1]); a[3] = pack_bf16(dsv[1][2], dsv[1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bk[4];
+          ldsm_x4_t(bk, sK_a + 2u * ((kg * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + dp * 16 + 8 * (lane >> 4)));
+          mma16816(dq[2 * dp], a, bk[0], bk[1]);
+          mma16816(dq[2 * dp + 1], a, bk[2], bk[3]);
+        }
       }
     }
 #pragma unroll
@@ -394,18 +460,22 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   p.dout = (const __nv_bfloat16*)a.dout; p.lddo = a.lddo; p.do_bs = a.do_bstride;
   p.dq = (__nv_bfloat16*)a.dq; p.dk = (__nv_bfloat16*)a.dk; p.dv = (__nv_bfloat16*)a.dv;
   const int Sq_pad = (a.f.Sq + 15) & ~15, Sk_pad = (a.f.Sk + 15) & ~15;
-  const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (size_t)Sq_pad * (Sk_pad + 8) * 2 + (Sk_pad + 2 * Sq_pad) * 4;
-  HAMT_REQUIRE(smem <= 227 * 1024, "attn_bwd: sequence too long for the single-CTA backward kernel");
+  const bool is_long = Sq_pad > 128 || Sk_pad > 128;
+  const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (is_long ? 0 : (size_t)Sq_pad * (Sk_pad + 8) * 2) + (Sk_pad + 2 * Sq_pad) * 4;
+  HAMT_REQUIRE(smem <= 227 * 1024, "attn_bwd: sequence too long for the single-CTA backward kernel (Sq + Sk <= ~790)");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
     attr_set = true;
   }
   int nw = (Sk_pad > Sq_pad ? Sk_pad : Sq_pad) / 16;
   if (nw > 8) nw = 8;
-  launch_pdl(attn_bwd_kernel, a.f.B * a.f.heads, nw * 32, smem, st, p);
+  if (is_long) launch_pdl(attn_bwd_kernel<true>, a.f.B * a.f.heads, 256, smem, st, p);
+  else launch_pdl(attn_bwd_kernel<false>, a.f.B * a.f.heads, nw * 32, smem, st, p);
   return check_launch("attn_bwd_kernel");
 }
 

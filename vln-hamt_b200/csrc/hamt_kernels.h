@@ -95,4 +95,25 @@ int mean_pool_bwd(const float* dy, void* dx, int N, int P, int H, cudaStream_t s
 int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st);
 int mul_rows_bf16(const void* a, const void* b, void* out, int B, int S, int H, cudaStream_t st);  // out[b,s,:] = a[b,s,:]*b[b,:]
 
+// fused AdamW (+ global-norm clip, bf16 shadow refresh, gradient zeroing) over the flat arena; hamt_optim.cu
+struct AdamWArgs {
+  float* param; float* grad; float* exp_avg; float* exp_avg_sq; void* shadow;   // flat [total]; shadow (bf16) may be null
+  long long total;                         // elements, multiple of 64
+  const int* chunk_seg;                    // [total / 64] segment id of every 64-element chunk, -1 = padding
+  int nseg;
+  const unsigned char* seg_active;         // [nseg] 1 = the parameter has a gradient this step
+  const float* seg_wd;                     // [nseg] weight decay of the parameter's group
+  int* seg_step;                           // [nseg] per-parameter step counters (state["step"]), updated
+  float* seg_step_size;                    // [nseg] scratch
+  const float* lr;                         // device scalar: this step's learning rate
+  double beta1, beta2, eps;
+  int correct_bias;
+  float max_grad_norm;                     // <= 0: no clipping
+  int want_norm;                           // compute the global gradient norm even without clipping
+  int zero_grad;                           // zero the gradients of the active segments after use
+  float* workspace;                        // [adamw_workspace_floats()]: [0] = grad norm, [1] = clip coefficient, rest scratch
+};
+int adamw_workspace_floats(void);
+int adamw_step(const AdamWArgs& a, cudaStream_t st);
+
 }  // namespace hamt
