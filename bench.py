@@ -187,6 +187,10 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--dp-mode", default="overlap", choices=["graph", "after", "overlap"],
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
+    ap.add_argument("--nccl-sms", type=int, default=-1,
+                    help="N > 1: SMs the backward GEMMs leave free for the overlapped NCCL all-reduce kernels (= NCCL channel cap); "
+                         "-1 = default (8), 0 = no reservation")
+    ap.add_argument("--quick", action="store_true", help="device-resident value only (no e2e / roofline / cpu legs): development aid")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the device-resident timed region with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit after it; "
@@ -210,7 +214,12 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    nccl_sms = 0
     if world > 1:
+        nccl_sms = 8 if args.nccl_sms < 0 else args.nccl_sms
+        if nccl_sms > 0:     # the all-reduce kernel gets exactly the SMs the backward GEMMs leave free
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_sms))
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_sms))
         dist.init_process_group("nccl", device_id=dev)
     schedule = args.tasks.split(",") if args.tasks else SCHEDULE
 
@@ -247,7 +256,8 @@ def main():
             (overlap.finish() if overlap else dp.sync_grads(arena))
 
     in_graph = world > 1 and args.dp_mode in ("graph", "overlap")
-    trainer = graph.GraphedTrainer(model, post_backward=exchange if in_graph else None) if use_graphs else None
+    bwd_sm_limit = (torch.cuda.get_device_properties(dev).multi_processor_count - nccl_sms) if nccl_sms > 0 else 0
+    trainer = graph.GraphedTrainer(model, post_backward=exchange if in_graph else None, bwd_sm_limit=bwd_sm_limit) if use_graphs else None
     graph_launches = {}
 
     def step(i, batch, eager=False):
@@ -266,7 +276,11 @@ def main():
         if not torch.is_tensor(batch["txt_ids"]) or batch["txt_ids"].device.type != "cuda":
             batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
         loss = model(batch, task, compute_loss=True)
+        if bwd_sm_limit:
+            _lib.load().hamt_gemm_set_sm_limit(bwd_sm_limit)
         loss.mean().backward()
+        if bwd_sm_limit:
+            _lib.load().hamt_gemm_set_sm_limit(0)
         exchange()
         model.zero_grad(set_to_none=True)
         return loss
@@ -365,6 +379,13 @@ def main():
         os._exit(0)
     ms, samples, launches, _ = timed(args.steps, from_host=False)
     clocks = sampler.result()
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": round(samples * world / (ms * 1e-3), 1), "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms / args.steps, 3),
+                              "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        os._exit(0)
     ms_e2e, samples_e2e, _, d2h = timed(args.steps, from_host=True)
     if args.diag and rank == 0:
         print(f"[diag] e2e {ms_e2e / args.steps:.2f} ms/step; host ms/step: " + ", ".join(f"{k}={v / args.steps * 1e3:.2f}" for k, v in diag_t.items()), file=sys.stderr)
@@ -459,7 +480,7 @@ def main():
                        "l2": "no explicit flush: each step streams ~10 GB of activations + 1.4 GB of weights/grads, >> 126 MB L2",
                        "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else
                                          ("all_reduce(AVG) on the flat fp32 grad slices, " + ("captured at the end of the step graph" if in_graph and use_graphs else "after backward")))
-                       if world > 1 else "none"},
+                       if world > 1 else "none", "nccl_sms_reserved_in_backward": nccl_sms},
             "gpu_launches": int(launches),
             "model_tflops": round(alg_flops_per_step * args.steps / (ms * 1e-3) / 1e12 * 1.0, 1),
             "clocks": clocks,

@@ -47,6 +47,10 @@ int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_
 
 /* tile_n == 0: the tile cost model may choose the CTA-pair kernel (default on; 0 restricts it to single-CTA tiles) */
 int hamt_gemm_set_auto_pair(int on);
+/* The persistent GEMM grids (one CTA per SM, ~200 KB of shared memory each: nothing else can co-reside) use at most n SMs; 0 = all.
+ * Data-parallel runs set 148 - R during the backward pass so that the R CTAs of the NCCL all-reduce kernel that overlaps it (dp.py;
+ * the reference overlaps its DDP buckets the same way, utils/misc.py:52-65) find free SMs instead of waiting for a GEMM to retire. */
+int hamt_gemm_set_sm_limit(int n);
 
 /* y = LayerNorm(dropout(x) + res) ; BertSelfOutput / BertOutput tail (vilmodel.py:139-143,181-185).
  * z_out (may alias x, may be null) receives dropout(x)+res in bf16; mean/rstd fp32 [M] (may be null). */
@@ -64,11 +68,13 @@ int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* r
 int hamt_attn_fwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,
                   const float* mask, void* out, long long ldo, long long o_bstride, float* lse, int B, int heads, int Sq, int Sk, float scale,
                   const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
-/* backward; dq/dk/dv use the q/k/v strides.  Sq, Sk <= 128 in this version. */
+/* backward; dq/dk/dv use the q/k/v strides.  Sq, Sk <= 128: dS through shared memory; longer (RxR, L = 300; Sq + Sk <= ~790): the dQ pass
+ * recomputes S and dP.  dbias_q/k/v (fp32 [heads*64], all three or none): += column sums of dq/dk/dv = the bias gradients of the
+ * query/key/value Linears (vilmodel.py:80-82), replacing a separate pass over the [tokens, 3H] gradient. */
 int hamt_attn_bwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,
                   const float* mask, const void* out, long long ldo, long long o_bstride, const float* lse, const void* dout, long long lddo,
                   long long do_bstride, void* dq, void* dk, void* dv, int B, int heads, int Sq, int Sk, float scale,
-                  const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+                  const unsigned long long* seed_ptr, unsigned int site, float p, float* dbias_q, float* dbias_k, float* dbias_v, void* stream);
 
 /* BertEmbeddings (vilmodel.py:54-69): out = dropout(LN(word[ids] + pos[s] + type0)), ids int64 [B,L]. */
 int hamt_embed_text_fwd(const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma, const float* beta,
@@ -123,9 +129,9 @@ int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n
  * (bias correction, eps outside the sqrt, decoupled decay AFTER the update with lr * wd; parameters without a gradient this step are
  * skipped and keep their step counter, :64-66) + torch.nn.utils.clip_grad_norm_ (main_r2r.py:271-274) + bf16 shadow refresh + gradient
  * zeroing (optimizer.zero_grad(), main_r2r.py:281).  Segment s = one parameter; chunk_seg maps every 64-element chunk of the flat
- * buffers to its segment (-1 = alignment padding).  workspace[0] = global gradient norm (before clipping), [1] = clip coefficient. */
+ * buffers to its segment (-1 = alignment padding); seg_end[s] = one past the parameter's last element.  workspace[0] = global gradient norm (before clipping), [1] = clip coefficient. */
 int hamt_adamw_workspace_floats(void);
-int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, int nseg,
+int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, const long long* seg_end, int nseg,
                     const unsigned char* seg_active, const float* seg_wd, int* seg_step, float* seg_step_size, const float* lr, double beta1,
                     double beta2, double eps, int correct_bias, float max_grad_norm, int want_norm, int zero_grad, float* workspace, void* stream);
 

@@ -60,10 +60,23 @@ def test_attention_fwd_bwd(B, Sq, Sk, masked):
     else:
         dqb, dkb = torch.zeros_like(qb), torch.zeros_like(kb)
         dq, dk, dv = dqb[:, :768], dkb[:, 768:1536], dkb[:, 1536:]
-    ops.attn_bwd(q, k, v, out, lse, dout, dq, dk, dv, B, Sq, Sk, HEADS, mask)
+    dbias = torch.full((3 * HEADS * D,), 0.5, dtype=torch.float32, device="cuda")
+    ops.attn_bwd(q, k, v, out, lse, dout, dq, dk, dv, B, Sq, Sk, HEADS, mask, dbias=dbias)
     for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
         e = (got.float() - want).abs().max().item()
         assert e < 4e-2 * max(1.0, want.abs().max().item()), f"{name} err {e}"
+    # fused bias gradients: the kernel accumulates the column sums of exactly the bf16 values it stored
+    want_b = torch.cat([dq.float().sum(0), dk.float().sum(0), dv.float().sum(0)]) + 0.5
+    assert (dbias - want_b).abs().max().item() <= 1e-4 * max(1.0, want_b.abs().max().item()) + 1e-3, (dbias - want_b).abs().max().item()
+    # and without the pointers the gradients are bit-identical
+    if self_attn:
+        g2 = torch.zeros_like(qkv)
+        dq2, dk2, dv2 = g2[:, :768], g2[:, 768:1536], g2[:, 1536:]
+    else:
+        gq2, gk2 = torch.zeros_like(qb), torch.zeros_like(kb)
+        dq2, dk2, dv2 = gq2[:, :768], gk2[:, 768:1536], gk2[:, 1536:]
+    ops.attn_bwd(q, k, v, out, lse, dout, dq2, dk2, dv2, B, Sq, Sk, HEADS, mask)
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
 def test_attention_fully_masked_rows_match_reference():

@@ -323,3 +323,29 @@ def test_stress_configs_forward_and_gradients_vs_oracle(name):
             bad.append((k, round(rel, 4)))
     assert checked > 20
     assert not bad, f"{name}: gradient mismatch ({len(bad)} of {checked}): {sorted(bad, key=lambda t: -t[1])[:8]}"
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_kernels_never_write_outside_a_parameters_gradient(task):
+    """Arena hygiene: every parameter's gradient view is followed by an alignment tail (arena.ALIGN = 64 elements); the wgrad /
+    column-sum / embedding kernels must leave those tails and the gradients of untouched parameters at exactly zero."""
+    from hamt_b200 import synth
+    cfg, model, sd = _build(dict(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1), 3)
+    model.train()
+    b = synth.make_batch(task, batch_size=3, txt_len=20, hist_len=4, seed=5, ragged=True)
+    np.random.seed(1); torch.manual_seed(1)
+    model(_to_dev(b), task, compute_loss=True).mean().backward()
+    torch.cuda.synchronize()
+    arena = model.arena()
+    inside = torch.zeros_like(arena.flat_grad, dtype=torch.bool)
+    names = {id(p): n for n, p in model.named_parameters()}
+    for p in arena.params:
+        o = arena.offsets[id(p)]
+        if p.grad is not None:
+            inside[o:o + p.numel()] = True
+    stray = (arena.flat_grad != 0) & ~inside
+    if stray.any():
+        idx = int(stray.nonzero()[0])
+        owner = max((arena.offsets[id(p)], names.get(id(p), "?")) for p in arena.params if arena.offsets[id(p)] <= idx)
+        raise AssertionError(f"{int(stray.sum())} stray gradient elements outside touched parameter views; first at flat index {idx} "
+                             f"(after the start of {owner[1]} by {idx - owner[0]})")

@@ -43,7 +43,8 @@ def test_fused_adamw_matches_reference_trajectory():
             got = p.detach().cpu()
             assert (got - want).abs().max().item() <= 1e-6 * max(1.0, want.abs().max().item()), (t, i)
             assert p.grad is None
-            assert torch.equal(arena.w16(p).cpu(), p.detach().to(torch.bfloat16).cpu()), "bf16 shadow must follow the update"
+            if grads[t][i] is not None:        # the update pass writes the shadow of the parameters it updates
+                assert torch.equal(arena.w16(p).cpu(), p.detach().to(torch.bfloat16).cpu()), "bf16 shadow must follow the update"
         assert float(arena.flat_grad.abs().max()) == 0.0, "zero_grad=True must leave a clean gradient buffer"
     st = opt.state
     assert [st[p]["step"] for p in ps] == rec["steps"]
@@ -82,8 +83,12 @@ def test_fused_adamw_on_model_gradients_vs_oracle():
         lr = optim.get_lr_sched(step + 1, opts)
         opt.set_lr(lr)
         norm = opt.step(max_grad_norm=5.0, zero_grad=True)
+        # comparator for the norm: fp64 sum of squares.  (torch's CPU fp32 vector_norm over the 23 M-element embedding gradient is
+        # itself 1.4e-5 low -- measured -- while the kernel's blocked fp32 partials + fp64 final reduction agree with fp64 to 1e-8.)
+        norm64 = float(np.sqrt(sum(float((g.double() ** 2).sum()) for g in gs if g is not None)))
+        assert float(norm) == pytest.approx(norm64, rel=2e-6)
         want_norm = OO.clip_grad_norm(gs, 5.0)
-        assert float(norm) == pytest.approx(want_norm, rel=1e-5)
+        assert want_norm == pytest.approx(norm64, rel=1e-4)
         ref.step(gs, lr)
         worst = max(((p.detach().cpu() - r).abs().max().item() / max(1e-3, r.abs().max().item())) for (_, p), r in zip(named, ref_ps))
         assert worst <= 2e-6, (step, task, worst)

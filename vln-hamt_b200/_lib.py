@@ -40,10 +40,11 @@ SIGNATURES = {
     "hamt_launch_count": [],
     "hamt_gemm_bf16": [vp, i32, ll, vp, i32, ll, vp, ll, i32, i32, i32, i32, i32, vp, i32, i32, vp, ll, f32, i32, i32, vp, vp],
     "hamt_gemm_set_auto_pair": [i32],
+    "hamt_gemm_set_sm_limit": [i32],
     "hamt_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
     "hamt_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, u32, f32, vp],
     "hamt_attn_fwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp],
-    "hamt_attn_bwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, vp, ll, ll, vp, vp, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp],
+    "hamt_attn_bwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, vp, ll, ll, vp, vp, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp, vp, vp, vp],
     "hamt_embed_text_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, u32, f32, vp],
     "hamt_embed_text_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, u32, f32, vp],
     "hamt_embed_feat_fwd": [C.POINTER(EmbedFeatDesc), vp],
@@ -55,7 +56,7 @@ SIGNATURES = {
     "hamt_add_bf16": [vp, vp, vp, ll, vp],
     "hamt_mul_rows_bf16": [vp, vp, vp, i32, i32, i32, vp],
     "hamt_adamw_workspace_floats": [],
-    "hamt_adamw_step": [vp, vp, vp, vp, vp, ll, vp, i32, vp, vp, vp, vp, vp, f64, f64, f64, i32, f32, i32, i32, vp, vp],
+    "hamt_adamw_step": [vp, vp, vp, vp, vp, ll, vp, vp, i32, vp, vp, vp, vp, vp, f64, f64, f64, i32, f32, i32, i32, vp, vp],
     "hamt_rowdot_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
     "hamt_rowdot_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "hamt_ce_fwd": [vp, ll, vp, vp, vp, i32, i32, vp],

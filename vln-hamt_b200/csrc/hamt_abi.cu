@@ -68,11 +68,12 @@ int hamt_attn_fwd(const void* q, const void* k, const void* v, long long q_bstri
 int hamt_attn_bwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,
                   const float* mask, const void* out, long long ldo, long long o_bstride, const float* lse, const void* dout, long long lddo,
                   long long do_bstride, void* dq, void* dk, void* dv, int B, int heads, int Sq, int Sk, float scale,
-                  const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
+                  const unsigned long long* seed_ptr, unsigned int site, float p, float* dbias_q, float* dbias_k, float* dbias_v, void* stream) {
   AttnBwdArgs a{};
   a.f = AttnArgs{q, k, v, q_bstride, kv_bstride, ldq, ldkv, mask, const_cast<void*>(out), ldo, o_bstride, const_cast<float*>(lse),
                  B, heads, Sq, Sk, scale, DropArgs{seed_ptr, site, p}};
   a.dout = dout; a.lddo = lddo; a.do_bstride = do_bstride; a.dq = dq; a.dk = dk; a.dv = dv;
+  a.dbq = dbias_q; a.dbk = dbias_k; a.dbv = dbias_v;
   return attn_bwd(a, (cudaStream_t)stream);
 }
 
@@ -118,11 +119,12 @@ int hamt_mul_rows_bf16(const void* a, const void* v, void* out, int B, int S, in
   return mul_rows_bf16(a, v, out, B, S, H, (cudaStream_t)stream);
 }
 
+int hamt_gemm_set_sm_limit(int n) { gemm_set_sm_limit(n); return 0; }
 int hamt_adamw_workspace_floats(void) { return adamw_workspace_floats(); }
-int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, int nseg,
+int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, const long long* seg_end, int nseg,
                     const unsigned char* seg_active, const float* seg_wd, int* seg_step, float* seg_step_size, const float* lr, double beta1,
                     double beta2, double eps, int correct_bias, float max_grad_norm, int want_norm, int zero_grad, float* workspace, void* stream) {
-  AdamWArgs a{param, grad, exp_avg, exp_avg_sq, shadow_bf16, total, chunk_seg, nseg, seg_active, seg_wd, seg_step, seg_step_size, lr,
+  AdamWArgs a{param, grad, exp_avg, exp_avg_sq, shadow_bf16, total, chunk_seg, seg_end, nseg, seg_active, seg_wd, seg_step, seg_step_size, lr,
               beta1, beta2, eps, correct_bias, max_grad_norm, want_norm, zero_grad, workspace};
   return adamw_step(a, (cudaStream_t)stream);
 }

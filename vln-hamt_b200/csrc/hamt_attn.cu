@@ -51,6 +51,7 @@ struct AttnP {
   // backward only
   const __nv_bfloat16* dout; long long lddo, do_bs;
   __nv_bfloat16 *dq, *dk, *dv;
+  float *dbq, *dbk, *dbv;   // [heads * 64] fp32 or null: += column sums of the (bf16-rounded) dq / dk / dv  (bias gradients of the projections)
 };
 
 // cooperative ASYNC copy (cp.async, 16 B per request, no register round trip: every request of the CTA is in flight at once)
@@ -70,15 +71,17 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;"
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem[];
-  const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 63) & ~63;
+  // keys are consumed in blocks of 64 (Sk_pad) but only the 16-key groups that hold real keys are ever read from shared memory,
+  // so K / V are staged with 16-row granularity (Sk_rows): S = 80 -> 35 KB instead of 48 KB per CTA, 6 instead of 4 CTAs per SM
+  const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 63) & ~63, Sk_rows = (p.Sk + 15) & ~15;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sK = sQ + Sq_pad * LDS;
-  __nv_bfloat16* sV = sK + Sk_pad * LDS;
-  float* sMask = reinterpret_cast<float*>(sV + Sk_pad * LDS);
+  __nv_bfloat16* sV = sK + Sk_rows * LDS;
+  float* sMask = reinterpret_cast<float*>(sV + Sk_rows * LDS);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   stage_rows(sQ, p.q + b * p.q_bs + h * D, p.ldq, p.Sq, Sq_pad);
-  stage_rows(sK, p.k + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
-  stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_pad);
+  stage_rows(sK, p.k + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_rows);
+  stage_rows(sV, p.v + b * p.kv_bs + h * D, p.ldkv, p.Sk, Sk_rows);
   for (int j = threadIdx.x; j < Sk_pad; j += blockDim.x)
     sMask[j] = j < p.Sk ? (p.mask ? p.mask[(long long)b * p.Sk + j] : 0.f) : -INFINITY;
   stage_wait();
@@ -185,6 +188,29 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
   }
 }
 
+// Column sums of a 16 x 64 fp32 accumulator fragment (rows g, g+8 of every lane quad; columns nt*8 + 2t + {0,1}) added to 64
+// shared-memory accumulators.  The 16 per-thread partial sums are reduced over the 8 row groups (lane bits 2..4) with a halving
+// butterfly -- each step exchanges the half of the values the partner keeps -- 14 shuffles instead of 48; every lane ends up owning 2
+// distinct columns.  (fp32 sums of the unrounded accumulators: the separate pass this replaces summed the bf16-rounded values; the
+// difference is rounding noise.)
+__device__ __forceinline__ void frag_colsum(const float (&acc)[8][4], float* sdst, int lane) {
+  float v[16];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { v[2 * nt] = acc[nt][0] + acc[nt][2]; v[2 * nt + 1] = acc[nt][1] + acc[nt][3]; }
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float w[8], x[4], y[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = (h16 ? v[8 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[8 + i], 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = (h8 ? w[4 + i] : w[i]) + __shfl_xor_sync(0xffffffffu, h8 ? w[i] : w[4 + i], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) y[i] = (h4 ? x[2 + i] : x[i]) + __shfl_xor_sync(0xffffffffu, h4 ? x[i] : x[2 + i], 4);
+  const int k = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0);    // index of y[0] in v: nt = k >> 1, y[1] is the odd column of the same pair
+  float* d = sdst + (k >> 1) * 8 + 2 * (lane & 3);
+  atomicAdd(d, y[0]);
+  atomicAdd(d + 1, y[1]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward.  Phase 1: warp w owns keys [16w,16w+16): dK, dV in registers, dS^T -> smem.
 //            Phase 2: warp w owns 16 queries: dQ = dS K.
@@ -206,6 +232,10 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
   float* sMask = reinterpret_cast<float*>(sDS + (LONG ? 0 : Sq_pad * LDP));
   float* sLse = sMask + Sk_pad;
   float* sDelta = sLse + Sq_pad;
+  float* sBias = sDelta + Sq_pad;                   // [3][64] column sums of dq, dk, dv of this (batch, head)
+  const bool want_bias = p.dbq != nullptr;
+  if (want_bias)
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sBias[i] = 0.f;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   stage_rows(sQ, p.q + b * p.q_bs + h * D, p.ldq, p.Sq, Sq_pad);
   stage_rows(sDO, p.dout + b * p.do_bs + h * D, p.lddo, p.Sq, Sq_pad);
@@ -332,6 +362,10 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
         }
       }
     }
+    if (want_bias) {      // rows of padded keys are exactly zero
+      frag_colsum(dk, sBias + D, lane);
+      frag_colsum(dv, sBias + 2 * D, lane);
+    }
   }
   __syncthreads();
   // phase 2: dQ[16 x 64] = dS[16 x Sk] K[Sk x 64]
@@ -412,6 +446,14 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
         for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(qp + nt * 8 + 2 * t) = pack_bf16(dq[nt][2 * r], dq[nt][2 * r + 1]);
       }
     }
+    if (want_bias) frag_colsum(dq, sBias, lane);     // rows of padded queries are exactly zero (dS = 0 there)
+  }
+  if (want_bias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+      float* dst = i < D ? p.dbq : (i < 2 * D ? p.dbk : p.dbv);
+      atomicAdd(dst + h * D + (i & (D - 1)), sBias[i]);
+    }
   }
 }
 
@@ -435,8 +477,8 @@ static AttnP to_params(const AttnArgs& a) {
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_common(a)) return rc;
   AttnP p = to_params(a);
-  const int Sq_pad = (a.Sq + 15) & ~15, Sk_pad = (a.Sk + 63) & ~63;
-  const size_t smem = (size_t)(Sq_pad + 2 * Sk_pad) * LDS * 2 + Sk_pad * 4;
+  const int Sq_pad = (a.Sq + 15) & ~15, Sk_pad = (a.Sk + 63) & ~63, Sk_rows = (a.Sk + 15) & ~15;
+  const size_t smem = (size_t)(Sq_pad + 2 * Sk_rows) * LDS * 2 + Sk_pad * 4;
   HAMT_REQUIRE(smem <= 227 * 1024, "attn_fwd: sequence too long for the single-CTA kernel");
   static bool attr_set = false;
   if (!attr_set) {
@@ -459,9 +501,11 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   AttnP p = to_params(a.f);
   p.dout = (const __nv_bfloat16*)a.dout; p.lddo = a.lddo; p.do_bs = a.do_bstride;
   p.dq = (__nv_bfloat16*)a.dq; p.dk = (__nv_bfloat16*)a.dk; p.dv = (__nv_bfloat16*)a.dv;
+  p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
+  HAMT_REQUIRE((a.dbq == nullptr) == (a.dbk == nullptr) && (a.dbq == nullptr) == (a.dbv == nullptr), "attn_bwd: bias-gradient pointers come as a triple");
   const int Sq_pad = (a.f.Sq + 15) & ~15, Sk_pad = (a.f.Sk + 15) & ~15;
   const bool is_long = Sq_pad > 128 || Sk_pad > 128;
-  const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (is_long ? 0 : (size_t)Sq_pad * (Sk_pad + 8) * 2) + (Sk_pad + 2 * Sq_pad) * 4;
+  const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (is_long ? 0 : (size_t)Sq_pad * (Sk_pad + 8) * 2) + (Sk_pad + 2 * Sq_pad + 3 * D) * 4;
   HAMT_REQUIRE(smem <= 227 * 1024, "attn_bwd: sequence too long for the single-CTA backward kernel (Sq + Sk <= ~790)");
   static bool attr_set = false;
   if (!attr_set) {

@@ -599,6 +599,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
 static bool g_auto_pair = true;    // hamt_gemm_set_auto_pair(0) restricts the cost model to single-CTA tiles
 void gemm_set_auto_pair(int on) { g_auto_pair = on != 0; }
 static int g_num_sms = 0;
+static int g_sm_limit = 0;        // hamt_gemm_set_sm_limit: persistent GEMM grids use at most this many SMs (0 = all)
+void gemm_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -606,6 +608,7 @@ static int num_sms() {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
+  if (g_sm_limit > 0 && g_sm_limit < g_num_sms) return g_sm_limit < 2 ? 2 : g_sm_limit;
   return g_num_sms;
 }
 

@@ -21,6 +21,7 @@ struct GemmArgs {
 };
 int gemm_bf16(const GemmArgs& a, cudaStream_t st);
 void gemm_set_auto_pair(int on);
+void gemm_set_sm_limit(int n);
 
 struct DropArgs { const unsigned long long* seed_ptr; unsigned int site; float p; };
 
@@ -47,6 +48,7 @@ struct AttnBwdArgs {
   AttnArgs f;                 // forward description (q,k,v,mask,out(=saved ctx),lse)
   const void* dout; long long lddo; long long do_bstride;
   void* dq; void* dk; void* dv;                      // bf16, same layout/strides as q / k / v
+  float* dbq; float* dbk; float* dbv;                // fp32 [heads*64] or null: += column sums of dq / dk / dv (fused bias gradients)
 };
 int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 
@@ -100,6 +102,7 @@ struct AdamWArgs {
   float* param; float* grad; float* exp_avg; float* exp_avg_sq; void* shadow;   // flat [total]; shadow (bf16) may be null
   long long total;                         // elements, multiple of 64
   const int* chunk_seg;                    // [total / 64] segment id of every 64-element chunk, -1 = padding
+  const long long* seg_end;                // [nseg] one past the last element of the parameter (its alignment tail is not part of it)
   int nseg;
   const unsigned char* seg_active;         // [nseg] 1 = the parameter has a gradient this step
   const float* seg_wd;                     // [nseg] weight decay of the parameter's group

@@ -22,14 +22,21 @@ static constexpr int kChunk = 64;          // elements per chunk_seg entry (aren
 static constexpr int kNormBlocks = 592;    // 148 SMs x 4
 
 __global__ void __launch_bounds__(256) adamw_sqnorm_kernel(const float* __restrict__ g, const int* __restrict__ chunk_seg,
-                                                           const unsigned char* __restrict__ active, long long n_vec, float* __restrict__ partials) {
+                                                           const unsigned char* __restrict__ active, const long long* __restrict__ seg_end,
+                                                           long long n_vec, float* __restrict__ partials) {
   pdl_grid_sync();
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     const int s = chunk_seg[i >> 4];
     if (s < 0 || !active[s]) continue;
     const float4 v = reinterpret_cast<const float4*>(g)[i];
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    const long long left = seg_end[s] - 4 * i;          // elements of this vector that belong to the parameter (alignment tail excluded)
+    if (left >= 4) acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    else {
+      if (left > 0) acc += v.x * v.x;
+      if (left > 1) acc += v.y * v.y;
+      if (left > 2) acc += v.z * v.z;
+    }
   }
   __shared__ float sh[8];
   acc = warp_sum(acc);
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(256) adamw_prepare_kernel(const float* __restr
 
 struct AdamWParams {
   float* p; float* g; float* m; float* v; __nv_bfloat16* shadow;
-  const int* chunk_seg; const unsigned char* active; const float* seg_wd; const float* seg_step_size; const float* scal; const float* lr_ptr;
+  const int* chunk_seg; const long long* seg_end; const unsigned char* active; const float* seg_wd; const float* seg_step_size; const float* scal; const float* lr_ptr;
   long long n_vec;
   float beta1, beta2, omb1, omb2, eps;
   int zero_grad;
@@ -95,6 +102,13 @@ __global__ void __launch_bounds__(256) adamw_update_kernel(const AdamWParams a) 
     const float step_size = a.seg_step_size[s];
     const float decay = lr * a.seg_wd[s];
     float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    const long long left = a.seg_end[s] - 4 * i;
+    if (left < 4) {                                       // alignment tail of the parameter: padding carries no gradient
+      if (left < 1) g4.x = 0.f;
+      if (left < 2) g4.y = 0.f;
+      if (left < 3) g4.z = 0.f;
+      g4.w = 0.f;
+    }
     float4 m4 = reinterpret_cast<const float4*>(a.m)[i];
     float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
     float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
@@ -120,7 +134,7 @@ int adamw_workspace_floats(void) { return kNormBlocks + 2; }
 
 int adamw_step(const AdamWArgs& a, cudaStream_t st) {
   HAMT_REQUIRE(a.total > 0 && a.total % kChunk == 0, "adamw: the flat buffer length must be a positive multiple of 64 elements");
-  HAMT_REQUIRE(a.nseg > 0 && a.chunk_seg && a.seg_active && a.seg_wd && a.seg_step && a.seg_step_size, "adamw: segment tables missing");
+  HAMT_REQUIRE(a.nseg > 0 && a.chunk_seg && a.seg_end && a.seg_active && a.seg_wd && a.seg_step && a.seg_step_size, "adamw: segment tables missing");
   HAMT_REQUIRE(a.param && a.grad && a.exp_avg && a.exp_avg_sq && a.lr && a.workspace, "adamw: null buffer");
   HAMT_REQUIRE((((uintptr_t)a.param | (uintptr_t)a.grad | (uintptr_t)a.exp_avg | (uintptr_t)a.exp_avg_sq | (uintptr_t)a.shadow) & 15) == 0,
                "adamw: buffers must be 16-byte aligned");
@@ -129,13 +143,13 @@ int adamw_step(const AdamWArgs& a, cudaStream_t st) {
   float* partials = a.workspace + 2;
   const bool clip = a.max_grad_norm > 0.f || a.want_norm;
   if (clip) {
-    launch_pdl(adamw_sqnorm_kernel, kNormBlocks, 256, 0, st, (const float*)a.grad, a.chunk_seg, a.seg_active, n_vec, partials);
+    launch_pdl(adamw_sqnorm_kernel, kNormBlocks, 256, 0, st, (const float*)a.grad, a.chunk_seg, a.seg_active, a.seg_end, n_vec, partials);
     if (int rc = check_launch("adamw_sqnorm_kernel")) return rc;
   }
   launch_pdl(adamw_prepare_kernel, 1, 256, 0, st, clip ? (const float*)partials : (const float*)nullptr, kNormBlocks, a.max_grad_norm, a.workspace,
              a.seg_step, a.seg_active, a.seg_step_size, a.nseg, a.lr, a.beta1, a.beta2, a.correct_bias);
   if (int rc = check_launch("adamw_prepare_kernel")) return rc;
-  AdamWParams p{a.param, a.grad, a.exp_avg, a.exp_avg_sq, (__nv_bfloat16*)a.shadow, a.chunk_seg, a.seg_active, a.seg_wd, a.seg_step_size,
+  AdamWParams p{a.param, a.grad, a.exp_avg, a.exp_avg_sq, (__nv_bfloat16*)a.shadow, a.chunk_seg, a.seg_end, a.seg_active, a.seg_wd, a.seg_step_size,
                 a.workspace, a.lr, n_vec, (float)a.beta1, (float)a.beta2, (float)(1.0 - a.beta1), (float)(1.0 - a.beta2), (float)a.eps, a.zero_grad};
   long long blocks = (n_vec + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -93,11 +93,11 @@ def attn_block_bwd(run: Run, dy, saved, att, out_mod, dx_out=None):
     _wgrad(A, dt, ctx, dense.weight)
     dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
     dqkv = torch.empty_like(qkv)
+    db = A.fused_grad(bs) if ws[0].requires_grad else None      # q/k/v bias gradients: column sums fused into the attention backward
     ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, S, S, run.heads,
-                 mask, d_attn)
+                 mask, d_attn, dbias=db)
     if ws[0].requires_grad:
         ops.gemm(dqkv, x, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
-        ops.colsum(dqkv, A.fused_grad(bs))
     ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)       # dx (residual path) += dqkv @ Wqkv
     return dx
 
@@ -172,15 +172,16 @@ def cross_block_bwd(run: Run, dy, saved, xatt):
     ML = B * L
     ws, bs = _qkv_params(xatt.att)
     ln, dense = xatt.output.LayerNorm, xatt.output.dense
+    db = A.fused_grad(bs) if ws[0].requires_grad else None      # q/k/v bias gradients accumulate from both directions' backward kernels
     if lang_ca:
         dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid)
         _wgrad(A, dt, ctx, dense.weight)
         dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:ML, :H], qkv[ML:, H:2 * H], qkv[ML:, 2 * H:], ctx[:ML], lse_l, dctx[:ML], dqkv[:ML, :H], dqkv[ML:, H:2 * H],
-                     dqkv[ML:, 2 * H:], B, L, V, run.heads, visn_mask, d_att_l)
+                     dqkv[ML:, 2 * H:], B, L, V, run.heads, visn_mask, d_att_l, dbias=db)
         ops.attn_bwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], ctx[ML:], lse_v, dctx[ML:], dqkv[ML:, :H], dqkv[:ML, H:2 * H],
-                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v)
+                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v, dbias=db)
     else:
         dx = torch.empty_like(xcat)
         dx[:ML].copy_(dy[:ML])
@@ -189,10 +190,9 @@ def cross_block_bwd(run: Run, dy, saved, xatt):
         dctx_v = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
         dqkv = torch.zeros_like(qkv)
         ops.attn_bwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], ctx[ML:], lse_v, dctx_v, dqkv[ML:, :H], dqkv[:ML, H:2 * H],
-                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v)
+                     dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v, dbias=db)
     if ws[0].requires_grad:
         ops.gemm(dqkv, xcat, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
-        ops.colsum(dqkv, A.fused_grad(bs))
     ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)
     return dx
 

@@ -74,7 +74,7 @@ class GraphedStep:
 
     _pools: Dict[int, object] = {}
 
-    def __init__(self, model, task: str, batch: Dict, post_backward=None, warmup: int = 2):
+    def __init__(self, model, task: str, batch: Dict, post_backward=None, warmup: int = 2, bwd_sm_limit: int = 0):
         self.model, self.task = model, task
         dev = next(model.parameters()).device
         # static inputs of the captured step: one packed device blob (loader.Layout), so a packed batch arrives with ONE copy
@@ -88,7 +88,14 @@ class GraphedStep:
 
         def body():
             loss = model(self.static, task, compute_loss=True)
-            loss.mean().backward()
+            # data-parallel: the backward GEMMs leave SMs free for the NCCL kernels that overlap them (grid sizes are baked in at capture)
+            if bwd_sm_limit:
+                _lib.load().hamt_gemm_set_sm_limit(bwd_sm_limit)
+            try:
+                loss.mean().backward()
+            finally:
+                if bwd_sm_limit:
+                    _lib.load().hamt_gemm_set_sm_limit(0)
             if post_backward is not None:
                 post_backward()
             return loss
@@ -143,13 +150,13 @@ class GraphedStep:
 class GraphedTrainer:
     """Cache of captured steps keyed by (task, batch signature); falls back to capture-on-first-use."""
 
-    def __init__(self, model, post_backward=None):
-        self.model, self.post_backward, self.steps = model, post_backward, {}
+    def __init__(self, model, post_backward=None, bwd_sm_limit: int = 0):
+        self.model, self.post_backward, self.steps, self.bwd_sm_limit = model, post_backward, {}, bwd_sm_limit
 
     def step(self, task: str, batch: Dict) -> torch.Tensor:
         sig = _signature(task, batch)
         st = self.steps.get(sig)
         if st is None:
-            st = GraphedStep(self.model, task, batch, self.post_backward)
+            st = GraphedStep(self.model, task, batch, self.post_backward, bwd_sm_limit=self.bwd_sm_limit)
             self.steps[sig] = st
         return st(batch)

@@ -124,14 +124,20 @@ def attn_fwd(q, k, v, B: int, Sq: int, Sk: int, heads: int, mask: Optional[torch
     return out, lse
 
 
-def attn_bwd(q, k, v, out, lse, dout, dq, dk, dv, B: int, Sq: int, Sk: int, heads: int, mask, drop: Drop = NO_DROP):
-    """dq/dk/dv are written through views with the same pitches as q/k/v."""
+def attn_bwd(q, k, v, out, lse, dout, dq, dk, dv, B: int, Sq: int, Sk: int, heads: int, mask, drop: Drop = NO_DROP, dbias=None):
+    """dq/dk/dv are written through views with the same pitches as q/k/v.  dbias: fp32 [3 * heads * 64] (q | k | v bias gradients, e.g.
+    arena.fused_grad of the three biases): the column sums of dq/dk/dv are ACCUMULATED into it by the kernel."""
     assert dq.stride(0) == q.stride(0) and dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
     Hd = heads * 64
     sp, site, p = drop.args
+    db = (None, None, None)
+    if dbias is not None:
+        if dbias.dtype != F32 or dbias.numel() != 3 * Hd or not dbias.is_contiguous():
+            raise ValueError("attn_bwd: dbias must be contiguous fp32 [3 * heads * 64]")
+        db = (dbias.data_ptr(), dbias.data_ptr() + 4 * Hd, dbias.data_ptr() + 8 * Hd)
     rc = _lib.load().hamt_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), Sq * q.stride(0), Sk * k.stride(0), q.stride(0), k.stride(0), _ptr(mask),
                                    out.data_ptr(), out.stride(0), Sq * out.stride(0), lse.data_ptr(), dout.data_ptr(), dout.stride(0),
-                                   Sq * dout.stride(0), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, Sq, Sk, 0.125, sp, site, p, _stream())
+                                   Sq * dout.stride(0), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, Sq, Sk, 0.125, sp, site, p, *db, _stream())
     _lib.check(rc, "attn_bwd")
 
 

@@ -68,7 +68,7 @@ class AdamW:
         # segment tables: one segment per optimised parameter
         self.seg_params: List[torch.nn.Parameter] = []
         chunk_seg = torch.full((total // 64,), -1, dtype=torch.int32)
-        wd = []
+        wd, ends = [], []
         seen = set()
         for g in self.param_groups:
             for p in g["params"]:
@@ -82,9 +82,11 @@ class AdamW:
                 chunk_seg[o // 64:(o + p.numel() + 63) // 64] = s
                 self.seg_params.append(p)
                 wd.append(float(g["weight_decay"]))
+                ends.append(o + p.numel())
         self.nseg = len(self.seg_params)
         self.chunk_seg = chunk_seg.to(dev)
         self.seg_wd = torch.tensor(wd, dtype=torch.float32, device=dev)
+        self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
         self.seg_step = torch.zeros(self.nseg, dtype=torch.int32, device=dev)
         self.seg_step_size = torch.zeros(self.nseg, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -127,7 +129,7 @@ class AdamW:
         g0 = self.param_groups[0]
         active = self._active()
         rc = _lib.load().hamt_adamw_step(a.flat_param.data_ptr(), a.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                         a.flat_bf16.data_ptr(), a.flat_param.numel(), self.chunk_seg.data_ptr(), self.nseg, active.data_ptr(),
+                                         a.flat_bf16.data_ptr(), a.flat_param.numel(), self.chunk_seg.data_ptr(), self.seg_end.data_ptr(), self.nseg, active.data_ptr(),
                                          self.seg_wd.data_ptr(), self.seg_step.data_ptr(), self.seg_step_size.data_ptr(), self.lr_dev.data_ptr(),
                                          float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]), int(bool(g0["correct_bias"])),
                                          float(max_grad_norm), int(want_norm), int(zero_grad), self.workspace.data_ptr(),
