@@ -189,7 +189,7 @@ def main():
                     help="gradient exchange: captured at the end of the step graph / eager after the replay / per-layer overlap (eager only)")
     ap.add_argument("--nccl-sms", type=int, default=-1,
                     help="N > 1: SMs the backward GEMMs leave free for the overlapped NCCL all-reduce kernels (= NCCL channel cap); "
-                         "-1 = default (8), 0 = no reservation")
+                         "-1 = default (0 = no reservation)")
     ap.add_argument("--quick", action="store_true", help="device-resident value only (no e2e / roofline / cpu legs): development aid")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     ap.add_argument("--profile-range", action="store_true",
@@ -214,9 +214,13 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:      # torchrun exports OMP_NUM_THREADS=1: give the host-side batch / weight preparation its share of the cores back
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
     nccl_sms = 0
     if world > 1:
-        nccl_sms = 8 if args.nccl_sms < 0 else args.nccl_sms
+        # measured at N = 2 (profiles/r01_scale_n2.txt): reserving SMs for NCCL costs more GEMM time than the overlap gains
+        # (0: 8850, 8: 8481, 16: 8777 samples/s), so the default is no reservation; the knob stays for larger N
+        nccl_sms = 0 if args.nccl_sms < 0 else args.nccl_sms
         if nccl_sms > 0:     # the all-reduce kernel gets exactly the SMs the backward GEMMs leave free
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_sms))
             os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_sms))
@@ -384,8 +388,12 @@ def main():
             print(json.dumps({"quick": True, "value": round(samples * world / (ms * 1e-3), 1), "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms / args.steps, 3),
                               "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "clocks": clocks}), flush=True)
         if world > 1:
-            dist.barrier(); dist.destroy_process_group()
-        os._exit(0)
+            if trainer is not None:
+                trainer.steps.clear()          # captured graphs hold NCCL work: destroy_process_group hangs while they are alive
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     ms_e2e, samples_e2e, _, d2h = timed(args.steps, from_host=True)
     if args.diag and rank == 0:
         print(f"[diag] e2e {ms_e2e / args.steps:.2f} ms/step; host ms/step: " + ", ".join(f"{k}={v / args.steps * 1e3:.2f}" for k, v in diag_t.items()), file=sys.stderr)
@@ -461,10 +469,12 @@ def main():
     gemm_ms = gemm_us * 1e-3
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
     peaks = load_peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    # DRAM bytes per launch of the most expensive GEMM signature, from the committed ncu --set full capture (profiles/r01_traffic.json)
+    traffic, traffic_of = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic, traffic_of = tj.get("dram_bytes_per_launch"), {"signature": tj.get("signature"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"), "source": tj.get("source")}
 
     if rank == 0:
         value = samples * world / (ms * 1e-3)
@@ -489,7 +499,7 @@ def main():
                     "graphs_captured_in_timed_regions": n_graphs1 - n_graphs0,
                     "how": "packed pinned host batch -> one cudaMemcpyAsync on a copy stream, 2 batches ahead (PrefetchLoader style, hamt_b200.loader) -> captured step -> per-step loss through a pinned slot + event (read one step behind)"},
             "roofline": {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": round(achieved_tf, 1), "peak": peaks["tf_sustained"],
-                         "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf_sustained"], 3), "traffic": traffic, "peak_source": peaks["src"] + " (sustained)",
+                         "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf_sustained"], 3), "traffic": traffic, "traffic_of": traffic_of, "peak_source": peaks["src"] + " (sustained)",
                          "launches": n_gemm, "share_of_step": round(gemm_ms / n_prof / (ms / args.steps), 3),
                          "how": "sum of 2*M*N*K over every GEMM launch of one pass over the task schedule / sum of their durations; each distinct "
                                 "GEMM signature of the pass is timed with CUDA events around a graph of 4 back-to-back launches on its real operands"},

@@ -65,9 +65,15 @@ def test_attention_fwd_bwd(B, Sq, Sk, masked):
     for got, want, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
         e = (got.float() - want).abs().max().item()
         assert e < 4e-2 * max(1.0, want.abs().max().item()), f"{name} err {e}"
-    # fused bias gradients: the kernel accumulates the column sums of exactly the bf16 values it stored
-    want_b = torch.cat([dq.float().sum(0), dk.float().sum(0), dv.float().sum(0)]) + 0.5
-    assert (dbias - want_b).abs().max().item() <= 1e-4 * max(1.0, want_b.abs().max().item()) + 1e-3, (dbias - want_b).abs().max().item()
+    # fused bias gradients: fp32 column sums of the unrounded dq / dk / dv accumulators, ACCUMULATED onto the buffer.  Against the fp32
+    # autograd sums with the tolerance of the gradients themselves, and against the sums of the stored bf16 values up to their
+    # rounding noise (2^-9 relative per element, random sign: ~ sqrt(rows) * 2^-9 * |element|).
+    want_b = torch.cat([qr.grad.sum(0), kr.grad.sum(0), vr.grad.sum(0)]) + 0.5
+    assert (dbias - want_b).abs().max().item() <= 4e-2 * max(1.0, want_b.abs().max().item())
+    stored_b = torch.cat([dq.float().sum(0), dk.float().sum(0), dv.float().sum(0)]) + 0.5
+    rows = B * max(Sq, Sk)
+    elem = max(dq.float().abs().max().item(), dk.float().abs().max().item(), dv.float().abs().max().item())
+    assert (dbias - stored_b).abs().max().item() <= 4 * (rows ** 0.5) * 2.0 ** -9 * elem + 1e-3
     # and without the pointers the gradients are bit-identical
     if self_attn:
         g2 = torch.zeros_like(qkv)

@@ -42,8 +42,9 @@ def timeit(fn, n=10, warm=2):          # noqa: F811 -- graph-timed: no CPU launc
 
 def main():
     res = []
-    for (M, N, K) in [(34560, 768, 768), (34560, 2304, 768), (34560, 3072, 768), (34560, 768, 3072), (5120, 768, 768), (5120, 2304, 768),
-                      (5120, 3072, 768), (5120, 768, 3072), (8512, 2304, 768), (3392, 3072, 768)]:
+    shapes = [] if "--no-gemm" in sys.argv else [(34560, 768, 768), (34560, 2304, 768), (34560, 3072, 768), (34560, 768, 3072), (5120, 768, 768), (5120, 2304, 768),
+                      (5120, 3072, 768), (5120, 768, 3072), (8512, 2304, 768), (3392, 3072, 768)]
+    for (M, N, K) in shapes:
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
@@ -74,7 +75,9 @@ def main():
         dout = torch.randn_like(out)
         dqkv = torch.zeros_like(qkv)
         t2 = timeit(lambda: ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:B * Sq, :768], dqkv[:B * Sk, 768:1536], dqkv[:B * Sk, 1536:], B, Sq, Sk, 12, None))
-        print(json.dumps({"attn": [B, Sq, Sk], "fwd_us": round(t * 1e3, 1), "bwd_us": round(t2 * 1e3, 1),
+        db = torch.zeros(2304, device="cuda")
+        t3 = timeit(lambda: ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:B * Sq, :768], dqkv[:B * Sk, 768:1536], dqkv[:B * Sk, 1536:], B, Sq, Sk, 12, None, dbias=db))
+        print(json.dumps({"attn": [B, Sq, Sk], "fwd_us": round(t * 1e3, 1), "bwd_us": round(t2 * 1e3, 1), "bwd_dbias_us": round(t3 * 1e3, 1),
                           "fwd_GBs": round((B * (Sq + 2 * Sk) * 768 * 2 + B * Sq * 768 * 2) / t / 1e6, 1)}), flush=True)
     # layernorm
     for M in (34560, 5120):
