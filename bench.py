@@ -505,9 +505,11 @@ def main():
                                 "GEMM signature of the pass is timed with CUDA events around a graph of 4 back-to-back launches on its real operands"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            sps, dt, threads = cpu_reference_samples_per_sec(2, 1, args.ref_batch, tasks=["sap", "mlm"])
+            # bounded sample of the SAME workload: two passes over the 12-step task schedule at batch 8 (ITM 4), ~10-20 s of CPU work
+            sps, dt, threads = cpu_reference_samples_per_sec(2 * len(SCHEDULE), 2, 2 * args.ref_batch)
             line["cpu_baseline"] = {"value": round(sps, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle port fp32 fwd+bwd, 1 SAP + 1 MLM step at batch {args.ref_batch} ({dt:.1f} s)"}
+                                    "sample": f"oracle port (fp32 torch CPU autograd of oracle/hamt_oracle.py), fwd+bwd, {2 * len(SCHEDULE)} steps of the 6-task schedule "
+                                              f"at batch {2 * args.ref_batch} (ITM {args.ref_batch}) after 2 warm-up steps ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         try:
