@@ -124,6 +124,10 @@ int hamt_ce_bwd(const float* logits, long long ld, const long long* labels, cons
                 long long ld_d, int M, int N, void* stream);
 int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);   /* out[i] = x[idx[i]] */
 int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream);  /* out[idx[i]] = x[i] */
+/* device-side batch assembly from a resident bf16 feature table [x_rows, H] (replaces np.stack + pad_tensors of
+ * pretrain_src/data/r2r_data.py:264-329, data/common.py:5-20 and the 106 MB host->device copy per batch): out[i] = idx[i] >= 0 ?
+ * x[idx[i]] : 0.  Indices are NOT range-checked on the device; the host wrapper checks them. */
+int hamt_gather_rows_pad_bf16(const void* x, long long x_rows, const long long* idx, void* out, long long n, int H, void* stream);
 
 /* fused optimizer step over the flat parameter arena: HF-style AdamW exactly as pretrain_src/optim/adamw.py:53-110
  * (bias correction, eps outside the sqrt, decoupled decay AFTER the update with lr * wd; parameters without a gradient this step are

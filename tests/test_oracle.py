@@ -187,3 +187,36 @@ def test_optim_oracle_matches_live_reference_schedule():
     from hamt_b200 import optim as ours
     for step in range(0, 30):
         assert OO.warmup_linear(step, 5, 20) == ref_wl(step, 5, 20) == ours.warmup_linear(step, 5, 20)
+
+
+def test_feature_oracle_matches_reference_golden():
+    """oracle/feature_oracle.py (history / observation feature assembly + padding) against tests/golden/feature_assembly.pt, which
+    oracle/make_golden_features.py produced by calling the UNMODIFIED reference methods (r2r_data.py get_history_feature /
+    get_ob_pano_view / get_all_point_angle_feature, common.pad_tensors): bit-exact.  The product's angle table too."""
+    from oracle import feature_oracle as FO
+    from oracle import make_golden_features as G
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import feature_store
+    rec = torch.load(os.path.join(GOLD, "feature_assembly.pt"))
+    keys, feats = G.scenario()
+    fts = {k: feats[i] for i, k in enumerate(keys)}
+    hs = [FO.history(fts, G.SCAN, s["path"], s["views"], s["t_cur"], G.D, G.A) for s in G.SAMPLES]
+    obs = [FO.observation(fts, G.SCAN, s["path"][s["t_cur"]], s["views"][s["t_cur"]], G.D, G.A) for s in G.SAMPLES]
+    for i, name in enumerate(["hist_img_fts", "hist_pano_img_fts", "hist_pano_ang_fts", "hist_img_probs"]):
+        assert np.array_equal(FO.pad([h[i] for h in hs]), rec[name].numpy()), name
+    assert np.array_equal(np.stack([o[0] for o in obs]), rec["ob_img_fts"].numpy())
+    assert np.array_equal(np.stack([o[1] for o in obs]), rec["ob_ang_fts"].numpy())
+    assert np.array_equal(np.stack([FO.point_angle_feature(G.A, b) for b in range(36)]), rec["angle_features"].numpy())
+    assert torch.equal(feature_store.point_angle_features(G.A), rec["angle_features"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pretrain_src/data"), reason="reference checkout not present on this machine")
+def test_feature_golden_regenerates_from_live_reference():
+    """The committed fixture is what the reference produces today (guards against a stale golden file)."""
+    from oracle import make_golden_features as G
+    rec = torch.load(os.path.join(GOLD, "feature_assembly.pt"))
+    db, common = G.reference_db()
+    s = G.SAMPLES[0]
+    rel = [np.zeros(2, np.float32)] * len(s["path"])
+    h = db.get_history_feature(G.SCAN, s["path"], s["views"], rel, s["t_cur"], return_img_probs=True)
+    assert np.array_equal(h[2], rec["hist_pano_img_fts"][0].numpy()) and np.array_equal(h[3], rec["hist_pano_ang_fts"][0].numpy())

@@ -63,6 +63,7 @@ SIGNATURES = {
     "hamt_ce_bwd": [vp, ll, vp, vp, vp, vp, vp, ll, i32, i32, vp],
     "hamt_gather_rows_bf16": [vp, vp, vp, i32, i32, vp],
     "hamt_scatter_rows_bf16": [vp, vp, vp, i32, i32, vp],
+    "hamt_gather_rows_pad_bf16": [vp, ll, vp, vp, ll, i32, vp],
 }
 _RESTYPES = {"hamt_last_error": C.c_char_p, "hamt_launch_count": ll}
 

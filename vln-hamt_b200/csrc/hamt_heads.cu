@@ -129,6 +129,23 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const lo
   }
 }
 
+// out[i,:] = idx[i] >= 0 ? x[idx[i],:] : 0   (rows of H bf16, H % 8 == 0).  Device-side batch assembly from a resident feature table
+// (SURVEY 8 f4): replaces the host-side np.stack / pad_tensors of pretrain_src/data/r2r_data.py:264-329 + common.py:5-20; padded
+// history steps and "killed" observations (r2r_tasks.py:322-324) are zero rows.
+__global__ void gather_rows_pad_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                       long long n, int H) {
+  pdl_grid_sync();
+  const int per_row = H / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * per_row; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per_row;
+    const int c = (int)(i % per_row) * 8;
+    const long long src = idx[r];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src >= 0) v = *reinterpret_cast<const uint4*>(x + src * H + c);
+    *reinterpret_cast<uint4*>(out + r * H + c) = v;
+  }
+}
+
 }  // namespace hamt
 
 using namespace hamt;
@@ -173,6 +190,15 @@ int hamt_gather_rows_bf16(const void* x, const long long* idx, void* out, int n,
   if (grid > 148 * 8) grid = 148 * 8;
   launch_pdl(gather_rows_kernel, grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H, 0);
   return check_launch("gather_rows_kernel");
+}
+int hamt_gather_rows_pad_bf16(const void* x, long long x_rows, const long long* idx, void* out, long long n, int H, void* stream) {
+  if (n <= 0) return 0;
+  HAMT_REQUIRE(H % 8 == 0 && x_rows > 0, "gather_rows_pad: H must be a multiple of 8 and the table non-empty");
+  HAMT_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "gather_rows_pad: table and output must be 16-byte aligned");
+  long long grid = (n * (H / 8) + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  launch_pdl(gather_rows_pad_kernel, (int)grid, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, idx, (__nv_bfloat16*)out, n, H);
+  return check_launch("gather_rows_pad_kernel");
 }
 int hamt_scatter_rows_bf16(const void* x, const long long* idx, void* out, int n, int H, void* stream) {
   if (n <= 0) return 0;

@@ -295,3 +295,19 @@ def scatter_rows(x: torch.Tensor, idx: torch.Tensor, rows: int) -> torch.Tensor:
     out = torch.zeros((rows, H), dtype=BF16, device=x.device)
     _lib.check(_lib.load().hamt_scatter_rows_bf16(x.data_ptr(), idx.data_ptr(), out.data_ptr(), n, H, _stream()), "scatter_rows")
     return out
+
+
+def gather_rows_pad(table: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = table[idx[i]] if idx[i] >= 0 else 0.  table: bf16 [R, H] contiguous, idx: int64 (any shape) on the same device.
+    The caller guarantees idx < R (feature_store checks on the host where the indices are built)."""
+    if table.dtype != BF16 or table.dim() != 2 or not table.is_contiguous():
+        raise ValueError("gather_rows_pad: table must be contiguous bf16 [R, H]")
+    if idx.dtype != torch.int64 or idx.device != table.device or not idx.is_contiguous():
+        raise ValueError("gather_rows_pad: idx must be a contiguous int64 tensor on the table's device")
+    n, H = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, H), dtype=BF16, device=table.device)
+    elif out.dtype != BF16 or out.numel() != n * H or not out.is_contiguous():
+        raise ValueError("gather_rows_pad: out must be contiguous bf16 with n * H elements")
+    _lib.check(_lib.load().hamt_gather_rows_pad_bf16(table.data_ptr(), table.shape[0], idx.data_ptr(), out.data_ptr(), n, H, _stream()), "gather_rows_pad")
+    return out
