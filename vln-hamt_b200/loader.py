@@ -115,7 +115,7 @@ class LossReader:
     def push(self, value: torch.Tensor):
         assert self.head - self.tail < self.depth, "LossReader ring full: pop() before pushing more"
         s = self.head % self.depth
-        self.buf[s:s + 1].copy_(value.reshape(1), non_blocking=True)
+        self.buf[s:s + 1].copy_(value.detach().reshape(1), non_blocking=True)     # detach: the ring must not join the autograd graph
         self.events[s].record()
         self.head += 1
 
