@@ -51,6 +51,9 @@ int hamt_gemm_set_auto_pair(int on);
  * Data-parallel runs set 148 - R during the backward pass so that the R CTAs of the NCCL all-reduce kernel that overlaps it (dp.py;
  * the reference overlaps its DDP buckets the same way, utils/misc.py:52-65) find free SMs instead of waiting for a GEMM to retire. */
 int hamt_gemm_set_sm_limit(int n);
+/* EXPERIMENTAL (default off, unmeasured): 16 epilogue warps on 32-column half groups for the ALU-bound GELU / dGELU / accumulate epilogues of
+ * fully aligned 256-wide tiles (hamt_gemm.cu: epilogue_wide).  Results are identical to the default epilogue. */
+int hamt_gemm_set_wide_epilogue(int on);
 
 /* y = LayerNorm(dropout(x) + res) ; BertSelfOutput / BertOutput tail (vilmodel.py:139-143,181-185).
  * z_out (may alias x, may be null) receives dropout(x)+res in bf16; mean/rstd fp32 [M] (may be null). */

@@ -62,7 +62,8 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+template <int THREADS = kEpiThreads>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // 16-byte chunk `c` of row `r` inside a warp's [32][128 B] staging tile (XOR swizzle -> conflict-free both ways)
 __device__ __forceinline__ uint32_t stage_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
@@ -81,10 +82,164 @@ enum : int {
   EPI_F32 = 5         // fp32 store / RMW / split-K red                                       (wgrad, logits)
 };
 
-// 320 threads, one CTA per SM: __launch_bounds__(320, 1) would cap ptxas at 168 registers (it sizes for 384 threads) and the
-// dGELU / accumulate epilogues spilled; 200 x 320 = 64 000 registers still fit the 64 K file.
-template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL wide epilogue (EW = 16; opt-in through hamt_gemm_set_wide_epilogue, not selected by default, not yet measured).
+// The GELU / dGELU epilogues are ALU-bound (2 MUFU + ~20 ALU per element; profiles/r01_ncu_ffn_gemms_v6.txt: 272 us against a
+// 116 us tensor-pipe floor at M = 34 560) and with 8 warps only two warps per scheduler hide each other's latencies (issue slots
+// 36 % busy).  Here 16 warps share a 128 x 256 accumulator: warp e owns TMEM lane quarter (warp & 3) and the 64-column slice e >> 2,
+// processed as two 32-column half groups so that the live state fits the 96-register budget of 18 warps.  Staging tile per warp:
+// [32 rows][64 B], chunk index XOR ((row >> 1) & 3): conflict-free for the row-owner accesses and for the coalesced phase (8 rows
+// x 64 B per instruction).  Only fully aligned problems are dispatched here (M % tile rows == 0, N % 256 == 0, 16-byte aligned
+// pitches), so there are no guards.
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t stage_off32(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+template <int BN, bool PAIR, int EPI>
+__device__ __forceinline__ void epilogue_wide(const GemmParams& p, uint8_t* staging, float* sbias, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, uint32_t rank, int u_first, int u_stride, int units, int warp, int lane) {
+  static_assert(BN == 256, "wide epilogue: 128 x 256 accumulators only");
+  static_assert(EPI == EPI_STORE || EPI == EPI_GELU_PRE || EPI == EPI_DGELU || EPI == EPI_ACCUM, "wide epilogue: bf16 store paths only");
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  constexpr int kET = 16 * 32;
+  const int e = warp - 2;
+  const int quarter = warp & 3;
+  const int slice = e >> 2;                       // 64-column slice of the tile
+  const int et = (int)threadIdx.x - 64;
+  uint8_t* stg = staging + e * (32 * 64);
+  const int r_co = lane >> 2, c_co = lane & 3;    // coalesced phase: 8 rows x 4 chunks of 16 B per instruction
+  const bool has_bias = p.bias != nullptr;
+  const bool do_colsum = EPI == EPI_DGELU && p.colsum != nullptr;
+  const __nv_bfloat16* pre_src = EPI == EPI_DGELU ? p.aux : (EPI == EPI_ACCUM ? reinterpret_cast<const __nv_bfloat16*>(p.out) : nullptr);
+  const long long pre_ld = EPI == EPI_DGELU ? p.ld_aux : p.ldo;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int u = u_first; u < units; u += u_stride) {
+    const int tn = u % p.tiles_n;
+    const int tm = (u / p.tiles_n) % p.tiles_m;
+    if (has_bias) {
+      if (et < BN) sbias[as * BN + et] = __ldg(p.bias + tn * BN + et);
+      epi_bar_sync<kET>();
+    }
+    const int row0 = tm * TM + (int)rank * BM + quarter * 32;
+    uint4 pre[4];
+    auto issue_pre = [&](int hg) {
+      const __nv_bfloat16* ap = pre_src + (long long)(row0 + r_co) * pre_ld + tn * BN + slice * 64 + hg * 32 + c_co * 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) pre[it] = *reinterpret_cast<const uint4*>(ap + (long long)(it * 8) * pre_ld);
+    };
+    if (EPI == EPI_DGELU || EPI == EPI_ACCUM) issue_pre(0);
+    mbar_wait(tfull0 + 8u * as, aphase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + slice * 64);
+    const float* bias_t = sbias + as * BN + slice * 64;
+#pragma unroll 1
+    for (int hg = 0; hg < 2; ++hg) {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + hg * 32, r);
+      tmem_ld_wait();
+      const int col0 = tn * BN + slice * 64 + hg * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_t + hg * 32 + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+      auto stage_own_row = [&]() {       // this lane's row (= its TMEM lane) -> 4 chunks of 8 bf16
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(stg + stage_off32(lane, c)) =
+              make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
+                         pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+      };
+      if (EPI == EPI_GELU_PRE) {
+        // the pre-activation goes out first (saved for the dGELU backward), then the activation through the same staging tile
+        stage_own_row();
+        __syncwarp();
+        __nv_bfloat16* ap = p.aux + (long long)(row0 + r_co) * p.ld_aux + col0 + c_co * 8;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          *reinterpret_cast<uint4*>(ap + (long long)(it * 8) * p.ld_aux) = *reinterpret_cast<const uint4*>(stg + stage_off32(it * 8 + r_co, c_co));
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (EPI == EPI_DGELU) {
+        // saved pre-activation: fetched coalesced (issue_pre), transposed through the staging tile so that every lane gets its row
+#pragma unroll
+        for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stg + stage_off32(it * 8 + r_co, c_co)) = pre[it];
+        __syncwarp();
+        if (hg == 0) issue_pre(1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off32(lane, c));
+          const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+          const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[c * 8 + j] *= dgelu_erf(a[j]);
+        }
+        __syncwarp();
+      }
+      stage_own_row();
+      __syncwarp();
+      float cs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)(row0 + r_co) * p.ldo + col0 + c_co * 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        uint4 w = *reinterpret_cast<const uint4*>(stg + stage_off32(it * 8 + r_co, c_co));
+        if (EPI == EPI_DGELU) {
+          if (do_colsum) {
+            const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+            cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y; cs[4] += f2.x; cs[5] += f2.y; cs[6] += f3.x; cs[7] += f3.y;
+          }
+        } else if (EPI == EPI_ACCUM) {     // gradient accumulation onto the residual-path gradient (old values prefetched)
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, os[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
+          uint32_t rs[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 x = unpack_bf16(ws[k]), y = unpack_bf16(os[k]);
+            rs[k] = pack_bf16(x.x + y.x, x.y + y.y);
+          }
+          w = make_uint4(rs[0], rs[1], rs[2], rs[3]);
+        }
+        *reinterpret_cast<uint4*>(op + (long long)(it * 8) * p.ldo) = w;
+      }
+      if (do_colsum) {      // warp-uniform; rows: 4 per thread above, then across the 8 row sub-groups (lane bits 2..4)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 4);
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        }
+        if (r_co == 0) {
+          float* cp = p.colsum + col0 + c_co * 8;
+          red_add_v4(cp, cs[0], cs[1], cs[2], cs[3]);
+          red_add_v4(cp + 4, cs[4], cs[5], cs[6], cs[7]);
+        }
+      }
+      __syncwarp();
+      if (EPI == EPI_ACCUM && hg == 0) issue_pre(1);      // old values of the second half group
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (!PAIR || rank == 0) mbar_arrive(tempty0 + 8u * as);
+      else mbar_arrive_cluster(mapa_u32(tempty0 + 8u * as, 0));
+    }
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+}
+
+// Register budget: 10 warps land 3 + 3 + 2 + 2 on the four SM sub-partitions (16 K registers each), so __launch_bounds__(320, 1) caps
+// ptxas at 168 registers; asking for more ("too many resources requested for launch") does not fit 3 warps x 32 lanes.
+// EW = epilogue warps: 8 (each warp owns a 32-row x BN/2 slab, 64-column groups) or 16 (EXPERIMENTAL wide epilogue, see epilogue_wide).
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI, int EW = kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using L = SmemLayout<BN, PAIR>;
   constexpr int TM = PAIR ? 2 * BM : BM;            // rows of the output tile owned by one CTA (pair)
@@ -115,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), PAIR ? 2 * kEpiWarps : kEpiWarps);
+      mbar_init(tempty_bar(s), PAIR ? 2 * EW : EW);
     }
     mbar_fence_init();
   }
@@ -227,6 +382,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
+  } else if constexpr (EW == 16) {
+    epilogue_wide<BN, PAIR, EPI>(p, smem_raw + L::kStagingOffset, reinterpret_cast<float*>(smem_raw + L::kBiasOffset), tmem_base,
+                                 tfull_bar(0), tempty_bar(0), rank, u_first, u_stride, units, warp, lane);
   } else {
     // ===================== epilogue warps =====================
     // The epilogue is specialised at compile time (EPI) for the combinations the hot path runs thousands of times per step, so
@@ -598,6 +756,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
 
 static bool g_auto_pair = true;    // hamt_gemm_set_auto_pair(0) restricts the cost model to single-CTA tiles
 void gemm_set_auto_pair(int on) { g_auto_pair = on != 0; }
+static bool g_wide_epi = false;    // hamt_gemm_set_wide_epilogue(1): EXPERIMENTAL 16-warp epilogue for aligned 256-wide bf16-store GEMMs
+void gemm_set_wide_epilogue(int on) { g_wide_epi = on != 0; }
 static int g_num_sms = 0;
 static int g_sm_limit = 0;        // hamt_gemm_set_sm_limit: persistent GEMM grids use at most this many SMs (0 = all)
 void gemm_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
@@ -612,10 +772,11 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI, int EW = kEpiWarps>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<BN, PAIR>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR, EPI>;
+  constexpr int kThreads = 64 + 32 * EW;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR, EPI, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -720,6 +881,25 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
     if (p.act == 0 && p.aux_mode == 0 && p.colsum == nullptr) epi = p.out_mode == 0 ? EPI_STORE : (p.out_mode == 1 ? EPI_ACCUM : EPI_GENERIC);
     else if (p.act == 1 && p.aux_mode == 1 && p.out_mode == 0 && p.colsum == nullptr) epi = EPI_GELU_PRE;
     else if (p.act == 0 && p.aux_mode == 2 && p.out_mode == 0) epi = EPI_DGELU;
+  }
+  // EXPERIMENTAL wide epilogue: fully aligned problems only (no guards in epilogue_wide)
+  if (g_wide_epi && bn == 256 && (epi == EPI_STORE || epi == EPI_GELU_PRE || epi == EPI_DGELU || epi == EPI_ACCUM)) {
+    const int tm_rows = pair ? 2 * BM : BM;
+    const bool aligned = a.M % tm_rows == 0 && a.N % 256 == 0 && (((uintptr_t)p.out | (uintptr_t)p.aux | (uintptr_t)p.colsum | (uintptr_t)p.bias) & 15) == 0 &&
+                         p.ldo % 8 == 0 && (p.aux == nullptr || p.ld_aux % 8 == 0);
+    if (aligned) {
+#define HAMT_WIDE(AMN_, BMN_, EPI_)                                                        \
+  if (a.a_mn == AMN_ && a.b_mn == BMN_ && epi == EPI_) {                                   \
+    if (pair) return launch<256, AMN_, BMN_, true, EPI_, 16>(ta, tb, p, st);               \
+    return launch<256, AMN_, BMN_, false, EPI_, 16>(ta, tb, p, st);                        \
+  }
+      HAMT_WIDE(false, false, EPI_STORE)
+      HAMT_WIDE(false, false, EPI_GELU_PRE)
+      HAMT_WIDE(false, true, EPI_STORE)
+      HAMT_WIDE(false, true, EPI_DGELU)
+      HAMT_WIDE(false, true, EPI_ACCUM)
+#undef HAMT_WIDE
+    }
   }
 #define HAMT_LAUNCH(BN_, AMN_, BMN_, PAIR_, EPI_) return launch<BN_, AMN_, BMN_, PAIR_, EPI_>(ta, tb, p, st);
 #define HAMT_DISPATCH(BN_, PAIR_)                                                                    \

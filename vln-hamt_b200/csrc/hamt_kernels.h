@@ -22,6 +22,7 @@ struct GemmArgs {
 int gemm_bf16(const GemmArgs& a, cudaStream_t st);
 void gemm_set_auto_pair(int on);
 void gemm_set_sm_limit(int n);
+void gemm_set_wide_epilogue(int on);
 
 struct DropArgs { const unsigned long long* seed_ptr; unsigned int site; float p; };
 
