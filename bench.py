@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--nccl-sms", type=int, default=-1,
                     help="N > 1: SMs the backward GEMMs leave free for the overlapped NCCL all-reduce kernels (= NCCL channel cap); "
                          "-1 = default (0 = no reservation)")
+    ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
+                    help="N > 1: dtype of the gradient all-reduce on the wire (bf16 = opt-in compressed exchange, unmeasured; default fp32 like DDP)")
     ap.add_argument("--quick", action="store_true", help="device-resident value only (no e2e / roofline / cpu legs): development aid")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches from Python instead of one CUDA graph per (task, batch signature)")
     ap.add_argument("--profile-range", action="store_true",
@@ -235,7 +237,7 @@ def main():
     arena.ensure()
     overlap = None
     if world > 1 and args.dp_mode == "overlap":
-        overlap = dp.LayerOverlap(arena)
+        overlap = dp.LayerOverlap(arena, wire_dtype=torch.bfloat16 if args.grad_wire == "bf16" else None)
         arena.layer_hook = overlap.layer_done
 
     B = args.batch
@@ -257,7 +259,7 @@ def main():
 
     def exchange():
         if world > 1:
-            (overlap.finish() if overlap else dp.sync_grads(arena))
+            (overlap.finish() if overlap else dp.sync_grads(arena, wire_dtype=torch.bfloat16 if args.grad_wire == "bf16" else None))
 
     in_graph = world > 1 and args.dp_mode in ("graph", "overlap")
     bwd_sm_limit = (torch.cuda.get_device_properties(dev).multi_processor_count - nccl_sms) if nccl_sms > 0 else 0
@@ -490,7 +492,7 @@ def main():
                        "l2": "no explicit flush: each step streams ~10 GB of activations + 1.4 GB of weights/grads, >> 126 MB L2",
                        "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else
                                          ("all_reduce(AVG) on the flat fp32 grad slices, " + ("captured at the end of the step graph" if in_graph and use_graphs else "after backward")))
-                       if world > 1 else "none", "nccl_sms_reserved_in_backward": nccl_sms},
+                       if world > 1 else "none", "nccl_sms_reserved_in_backward": nccl_sms, "grad_wire_dtype": args.grad_wire},
             "gpu_launches": int(launches),
             "model_tflops": round(alg_flops_per_step * args.steps / (ms * 1e-3) / 1e12 * 1.0, 1),
             "clocks": clocks,

@@ -98,7 +98,7 @@ def _free_port():
     return p
 
 
-def _dp_worker(rank, world, port, overlap):
+def _dp_worker(rank, world, port, overlap, wire=None):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import hamt_b200  # noqa: F401
@@ -115,12 +115,13 @@ def _dp_worker(rank, world, port, overlap):
     for i, p in enumerate(touched):                     # fake "backward": rank-dependent gradients written into the arena views
         arena.grad(p).fill_(float(rank + 1) * (i + 1))
     untouched = model.itm_head.net[0].weight
+    wire_dtype = torch.bfloat16 if wire == "bf16" else None          # opt-in compressed exchange (values here are bf16-exact)
     if overlap:
-        ov = dp.LayerOverlap(arena)
+        ov = dp.LayerOverlap(arena, wire_dtype=wire_dtype)
         ov.layer_done(layer)
         ov.finish()
     else:
-        n = dp.sync_grads(arena)
+        n = dp.sync_grads(arena, wire_dtype=wire_dtype)
         assert n >= sum(p.numel() for p in touched)
     mean = sum(range(1, world + 1)) / world
     for i, p in enumerate(touched):
@@ -133,6 +134,10 @@ def _dp_worker(rank, world, port, overlap):
 @pytest.mark.parametrize("overlap", [False, True])
 def test_data_parallel_grad_exchange_gloo_world2(overlap):
     mp.spawn(_dp_worker, args=(2, _free_port(), overlap), nprocs=2, join=True)
+
+
+def test_data_parallel_bf16_wire_exchange_gloo_world2():
+    mp.spawn(_dp_worker, args=(2, _free_port(), True, "bf16"), nprocs=2, join=True)
 
 
 def test_packed_batch_layout_roundtrip_on_cpu():

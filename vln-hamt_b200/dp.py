@@ -35,14 +35,25 @@ def _ranges(arena: ParamArena, params) -> List[Tuple[int, int]]:
     return out
 
 
-def _reduce(t: torch.Tensor, group):
-    """Average across ranks: NCCL has a native AVG; gloo (CPU tests) sums and the caller scales."""
+def _reduce(t: torch.Tensor, group, wire_dtype=None):
+    """Average across ranks: NCCL has a native AVG; gloo (CPU tests) sums and the caller scales.  wire_dtype (opt-in, e.g.
+    torch.bfloat16) sends a down-cast copy and writes the result back into the fp32 slice when the collective has finished --
+    half the bytes on the wire for two extra elementwise passes.  Returns (work, scale, wire_buffer)."""
+    buf = t if wire_dtype is None or wire_dtype == t.dtype else t.to(wire_dtype)
     if dist.get_backend(group) == "nccl":
-        return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True), None
-    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True), 1.0 / dist.get_world_size(group)
+        return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group, async_op=True), None, buf
+    return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True), 1.0 / dist.get_world_size(group), buf
 
 
-def sync_grads(arena: ParamArena, group=None, max_chunk: int = 64 << 20) -> int:
+def _finish(work, scale, buf, t):
+    work.wait()
+    if buf is not t:
+        t.copy_(buf)
+    if scale is not None:
+        t.mul_(scale)
+
+
+def sync_grads(arena: ParamArena, group=None, max_chunk: int = 64 << 20, wire_dtype=None) -> int:
     """All-reduce (average) the gradients touched in this step.  Returns the number of elements exchanged."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
@@ -50,20 +61,18 @@ def sync_grads(arena: ParamArena, group=None, max_chunk: int = 64 << 20) -> int:
     for a, b in _ranges(arena, arena._touched):
         for s in range(a, b, max_chunk):
             e = min(b, s + max_chunk)
-            works.append((_reduce(arena.flat_grad[s:e], group), arena.flat_grad[s:e]))
+            works.append((_reduce(arena.flat_grad[s:e], group, wire_dtype), arena.flat_grad[s:e]))
             total += e - s
-    for (w, scale), t in works:
-        w.wait()
-        if scale is not None:
-            t.mul_(scale)
+    for (w, scale, buf), t in works:
+        _finish(w, scale, buf, t)
     return total
 
 
 class LayerOverlap:
     """Reduce each layer's gradient slice as soon as that layer's backward is done."""
 
-    def __init__(self, arena: ParamArena, group=None):
-        self.arena, self.group = arena, group
+    def __init__(self, arena: ParamArena, group=None, wire_dtype=None):
+        self.arena, self.group, self.wire_dtype = arena, group, wire_dtype
         self.pending = []
         self.done_ids = set()
 
@@ -76,16 +85,14 @@ class LayerOverlap:
         for p in params:
             self.done_ids.add(id(p))
         for a, b in _ranges(self.arena, params):
-            self.pending.append((_reduce(self.arena.flat_grad[a:b], self.group), self.arena.flat_grad[a:b]))
+            self.pending.append((_reduce(self.arena.flat_grad[a:b], self.group, self.wire_dtype), self.arena.flat_grad[a:b]))
 
     def finish(self):
         """After backward: exchange whatever was not covered by a layer hook, then wait for everything."""
         rest = [p for p in self.arena._touched if id(p) not in self.done_ids]
         if rest and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             for a, b in _ranges(self.arena, rest):
-                self.pending.append((_reduce(self.arena.flat_grad[a:b], self.group), self.arena.flat_grad[a:b]))
-        for (w, scale), t in self.pending:
-            w.wait()
-            if scale is not None:
-                t.mul_(scale)
+                self.pending.append((_reduce(self.arena.flat_grad[a:b], self.group, self.wire_dtype), self.arena.flat_grad[a:b]))
+        for (w, scale, buf), t in self.pending:
+            _finish(w, scale, buf, t)
         self.pending, self.done_ids = [], set()
