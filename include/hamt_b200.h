@@ -107,6 +107,10 @@ typedef struct {
 int hamt_embed_feat_fwd(const hamt_embed_feat_desc* d, void* stream);
 int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_grads* g, void* stream);
 
+/* EXPERIMENTAL (default 0, unmeasured): 1 / 2 select ln_bwd_kernel_v2 (residual-gradient row prefetched with dy / z, bank-conflict-free
+ * shared accumulators; compiled for 1 / 2 resident CTAs per SM) -- same arithmetic as the default kernel. */
+int hamt_ln_set_variant(int v);
+
 /* streaming helpers */
 int hamt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);
 int hamt_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream);      /* out[n] += sum_m x[m,n] (bias grads) */

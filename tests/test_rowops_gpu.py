@@ -230,3 +230,37 @@ def test_head_pieces():
     assert torch.equal(gth, x[idx])
     sc = ops.scatter_rows(gth, idx, M)
     assert torch.equal(sc[idx], x[idx]) and sc.abs().sum().item() == x[idx].abs().sum().item()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HAMT_TEST_EXPERIMENTAL"), reason="experimental LayerNorm-backward variants: opt-in (HAMT_TEST_EXPERIMENTAL=1), off by default in the product")
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("H", [768, 512])
+def test_ln_bwd_experimental_variants_match_default(variant, H):
+    """hamt_ln_set_variant(1|2): same arithmetic, different scheduling -> dx / dres bit-identical to the default kernel (with dropout and a
+    residual-path gradient coming in), column sums equal up to fp32 summation order."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    M = 1500
+    x, res, dy, dri = (bf(torch.randn(M, H, generator=G(s))) for s in (1, 2, 3, 4))
+    gamma, beta = (1 + 0.1 * torch.randn(H, generator=G(5))).cuda(), torch.zeros(H, device="cuda")
+    seed = torch.tensor([77], dtype=torch.int64, device="cuda")
+    drop = ops.Drop(seed, site=3, p=0.1)
+    _, z, mean, rstd = ops.ln_fwd(x.clone(), res, gamma, beta, EPS, drop)
+
+    def run():
+        sums = [torch.zeros(H, device="cuda") for _ in range(3)]
+        dx, dres = ops.ln_bwd(dy, z, mean, rstd, gamma, *sums, dres_in=dri, drop=drop)
+        torch.cuda.synchronize()
+        return dx, dres, sums
+
+    dx0, dr0, s0 = run()
+    lib.hamt_ln_set_variant(variant)
+    try:
+        dx1, dr1, s1 = run()
+    finally:
+        lib.hamt_ln_set_variant(0)
+    assert torch.equal(dx0, dx1) and torch.equal(dr0, dr1)
+    for a, b in zip(s0, s1):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, a.abs().max().item())

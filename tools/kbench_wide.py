@@ -28,3 +28,18 @@ for M in (34560, 5120):
             row[f"{name} {'wide' if wide else 'base'} us"] = round(timeit(fn) * 1e3, 1)
     lib.hamt_gemm_set_wide_epilogue(0)
     print(json.dumps(row), flush=True)
+
+# LayerNorm backward: default kernel vs the experimental variants (hamt_ln_set_variant)
+for M in (34560, 8512, 5120, 3392):
+    x = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+    r = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+    gm, bt = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
+    y, z, mean, rstd = ops.ln_fwd(x.clone(), r, gm, bt, 1e-12)
+    dy, dri = torch.randn(M, 768, device="cuda").to(torch.bfloat16), torch.randn(M, 768, device="cuda").to(torch.bfloat16)
+    dg, db, dbias = (torch.zeros(768, device="cuda") for _ in range(3))
+    row = {"ln_bwd_M": M}
+    for v in (0, 1, 2):
+        lib.hamt_ln_set_variant(v)
+        row[f"variant{v}_us"] = round(timeit(lambda: ops.ln_bwd(dy, z, mean, rstd, gm, dg, db, dbias, dres_in=dri)) * 1e3, 1)
+    lib.hamt_ln_set_variant(0)
+    print(json.dumps(row), flush=True)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "hamt_embed_text_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, u32, f32, vp],
     "hamt_embed_feat_fwd": [C.POINTER(EmbedFeatDesc), vp],
     "hamt_embed_feat_bwd": [C.POINTER(EmbedFeatDesc), C.POINTER(EmbedFeatGrads), vp],
+    "hamt_ln_set_variant": [i32],
     "hamt_cast_f32_to_bf16": [vp, vp, ll, vp],
     "hamt_colsum_bf16": [vp, ll, vp, i32, i32, vp],
     "hamt_mean_pool_fwd": [vp, vp, i32, i32, i32, vp],

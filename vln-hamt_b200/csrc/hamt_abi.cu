@@ -110,6 +110,7 @@ int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_gra
   return embed_feat_bwd(a, (cudaStream_t)stream);
 }
 
+int hamt_ln_set_variant(int v) { ln_set_variant(v); return 0; }
 int hamt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream) { return cast_f32_to_bf16(in, out, n, (cudaStream_t)stream); }
 int hamt_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream) { return colsum_bf16(x, ld, out, M, N, (cudaStream_t)stream); }
 int hamt_mean_pool_fwd(const void* x, float* out, int N, int P, int H, void* stream) { return mean_pool_fwd(x, out, N, P, H, (cudaStream_t)stream); }

@@ -91,6 +91,7 @@ struct EmbedFeatBwdArgs {
 int embed_feat_bwd(const EmbedFeatBwdArgs& a, cudaStream_t st);
 
 // misc bandwidth kernels
+void ln_set_variant(int v);
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 int colsum_bf16(const void* x, long long ld, float* out, int M, int N, cudaStream_t st);          // out[n] += sum_m x[m,n]
 int mean_pool_fwd(const void* x, float* out, int N, int P, int H, cudaStream_t st);                // bf16 [N,P,H] -> fp32 [N,H]

@@ -178,6 +178,97 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// EXPERIMENTAL variant of ln_bwd_kernel (opt-in through hamt_ln_set_variant(1); default off, unmeasured).  Same arithmetic, two
+// scheduling changes aimed at the small-M launches (M = 2.5 k .. 8.5 k rows, 26 us at 1.2 TB/s -- 40 of the 44 launches per step):
+//   * the residual-path gradient row (dres_in) is requested together with dy and z instead of after the two warp reductions
+//     (one exposed HBM latency per row less);
+//   * the cross-warp accumulators live in shared memory as [3][NCH*8][32] (value index major, lane minor) so the 72 shared atomics of
+//     every lane hit 32 consecutive banks; the row-major [3][H] layout of ln_bwd_kernel gives 8-way bank conflicts (lane stride 32 B).
+// OCC2: compile for two resident CTAs per SM (128 registers, some spills) instead of one (246 registers; the default kernel also needs
+// 238 and therefore runs 8 warps per SM) -- which of the two wins is a measurement for round 2.
+template <int NCH, bool OCC2>
+__global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                        const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
+                                                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                                                        float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
+  pdl_grid_sync();
+  constexpr int H = NCH * 256;
+  constexpr int NV = NCH * 8;                 // values per lane
+  __shared__ float sacc[3][NV][32];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const DropState ds = drop_init(dc);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&sacc[0][0][0])[i] = 0.f;
+  __syncthreads();
+  float g[NV];
+  load_vec_f32<NCH>(gamma, lane, g);
+  float acc_g[NV], acc_b[NV], acc_x[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    float d[NV], zz[NV], o[NV];
+    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
+    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
+    if (dres != nullptr && dres_in != nullptr) load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
+    else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) o[i] = 0.f;
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float xh = (zz[i] - mean) * rstd;
+      const float gd = d[i] * g[i];
+      acc_g[i] += d[i] * xh;
+      acc_b[i] += d[i];
+      s1 += gd;
+      s2 += gd * xh;
+      zz[i] = xh;
+      d[i] = gd;
+    }
+    s1 = warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+    float dz[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dz[i] = rstd * (d[i] - s1 - zz[i] * s2);
+    if (dres != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) o[i] += dz[i];
+      store_row_bf16<NCH>(dres + (long long)row * H, lane, o);
+    }
+    if (dx != nullptr) {
+      if (ds.on) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc_x[i] += dz[i];
+      store_row_bf16<NCH>(dx + (long long)row * H, lane, dz);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    atomicAdd(&sacc[0][i][lane], acc_g[i]);
+    atomicAdd(&sacc[1][i][lane], acc_b[i]);
+    atomicAdd(&sacc[2][i][lane], acc_x[i]);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
+    const int i = idx >> 5, l = idx & 31;                     // value i of lane l  ->  column (i / 8) * 256 + l * 8 + (i % 8)
+    const int col = (i >> 3) * 256 + l * 8 + (i & 7);
+    if (dgamma) atomicAdd(dgamma + col, sacc[0][i][l]);
+    if (dbeta) atomicAdd(dbeta + col, sacc[1][i][l]);
+    if (dbias) atomicAdd(dbias + col, sacc[2][i][l]);
+  }
+}
+
+static int g_ln_variant = 0;       // hamt_ln_set_variant: 0 = ln_bwd_kernel (default), 1 / 2 = ln_bwd_kernel_v2 with 1 / 2 CTAs per SM (experimental)
+void ln_set_variant(int v) { g_ln_variant = v; }
+
 static int grid_for_rows(int M, int wpb, int max_ctas) {
   int g = (M + wpb - 1) / wpb;
   return g < max_ctas ? (g < 1 ? 1 : g) : max_ctas;
@@ -204,6 +295,16 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
   const int grid = grid_for_rows(M, 8 * 4, 148 * 2);
   auto DY = (const __nv_bfloat16*)dy; auto Z = (const __nv_bfloat16*)z; auto DRI = (const __nv_bfloat16*)dres_in;
   auto DX = (__nv_bfloat16*)dx; auto DR = (__nv_bfloat16*)dres;
+  if (g_ln_variant == 1 || g_ln_variant == 2) {
+#define HAMT_LNV2(NCH_)                                                                                                        \
+  {                                                                                                                            \
+    if (g_ln_variant == 2) launch_pdl(ln_bwd_kernel_v2<NCH_, true>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc); \
+    else launch_pdl(ln_bwd_kernel_v2<NCH_, false>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);                  \
+  }
+    if (H == 768) HAMT_LNV2(3) else if (H == 512) HAMT_LNV2(2) else HAMT_LNV2(4)
+#undef HAMT_LNV2
+    return check_launch("ln_bwd_kernel_v2");
+  }
   if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
   else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
   else launch_pdl(ln_bwd_kernel<4>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
