@@ -108,7 +108,8 @@ int hamt_embed_feat_fwd(const hamt_embed_feat_desc* d, void* stream);
 int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_grads* g, void* stream);
 
 /* EXPERIMENTAL (default 0, unmeasured): 1 / 2 select ln_bwd_kernel_v2 (residual-gradient row prefetched with dy / z, bank-conflict-free
- * shared accumulators; compiled for 1 / 2 resident CTAs per SM) -- same arithmetic as the default kernel. */
+ * shared accumulators; compiled for 1 / 2 resident CTAs per SM), 3 selects ln_bwd_kernel_v3 (column sums accumulated in shared memory
+ * every row instead of in 72 registers per lane) -- same arithmetic as the default kernel. */
 int hamt_ln_set_variant(int v);
 
 /* streaming helpers */

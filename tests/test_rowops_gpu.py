@@ -233,7 +233,7 @@ def test_head_pieces():
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("HAMT_TEST_EXPERIMENTAL"), reason="experimental LayerNorm-backward variants: opt-in (HAMT_TEST_EXPERIMENTAL=1), off by default in the product")
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("H", [768, 512])
 def test_ln_bwd_experimental_variants_match_default(variant, H):
     """hamt_ln_set_variant(1|2): same arithmetic, different scheduling -> dx / dres bit-identical to the default kernel (with dropout and a

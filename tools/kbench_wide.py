@@ -38,7 +38,7 @@ for M in (34560, 8512, 5120, 3392):
     dy, dri = torch.randn(M, 768, device="cuda").to(torch.bfloat16), torch.randn(M, 768, device="cuda").to(torch.bfloat16)
     dg, db, dbias = (torch.zeros(768, device="cuda") for _ in range(3))
     row = {"ln_bwd_M": M}
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         lib.hamt_ln_set_variant(v)
         row[f"variant{v}_us"] = round(timeit(lambda: ops.ln_bwd(dy, z, mean, rstd, gm, dg, db, dbias, dres_in=dri)) * 1e3, 1)
     lib.hamt_ln_set_variant(0)

@@ -266,7 +266,87 @@ __global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv
   }
 }
 
-static int g_ln_variant = 0;       // hamt_ln_set_variant: 0 = ln_bwd_kernel (default), 1 / 2 = ln_bwd_kernel_v2 with 1 / 2 CTAs per SM (experimental)
+// EXPERIMENTAL variant 3: as v2, but the three column-sum accumulators are not kept in registers across rows (72 registers per lane,
+// the reason the kernels above need ~240 registers and run one CTA = 8 warps per SM): every row adds its 72 contributions per lane
+// straight into the conflict-free shared layout with shared-memory atomics (32 consecutive banks per instruction).  Aim: <= 128
+// registers without spills -> 2 CTAs per SM, twice the loads in flight.
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                                                           const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                           const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
+                                                           __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                                                           float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
+  pdl_grid_sync();
+  constexpr int H = NCH * 256;
+  constexpr int NV = NCH * 8;
+  __shared__ float sacc[3][NV][32];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const DropState ds = drop_init(dc);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&sacc[0][0][0])[i] = 0.f;
+  __syncthreads();
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    float d[NV], zz[NV], o[NV];
+    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
+    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
+    const bool has_in = dres != nullptr && dres_in != nullptr;
+    if (has_in) load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8);
+      const float4 gb = *reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8 + 4);
+      const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = c * 8 + j;
+        const float xh = (zz[i] - mean) * rstd;
+        const float gd = d[i] * gg[j];
+        atomicAdd(&sacc[0][i][lane], d[i] * xh);
+        atomicAdd(&sacc[1][i][lane], d[i]);
+        s1 += gd;
+        s2 += gd * xh;
+        zz[i] = xh;
+        d[i] = gd;
+      }
+    }
+    s1 = warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) d[i] = rstd * (d[i] - s1 - zz[i] * s2);      // d <- dz
+    if (dres != nullptr) {
+      if (has_in) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i] += d[i];
+        store_row_bf16<NCH>(dres + (long long)row * H, lane, o);
+      } else {
+        store_row_bf16<NCH>(dres + (long long)row * H, lane, d);
+      }
+    }
+    if (dx != nullptr) {
+      if (ds.on) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) atomicAdd(&sacc[2][i][lane], d[i]);
+      store_row_bf16<NCH>(dx + (long long)row * H, lane, d);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
+    const int i = idx >> 5, l = idx & 31;
+    const int col = (i >> 3) * 256 + l * 8 + (i & 7);
+    if (dgamma) atomicAdd(dgamma + col, sacc[0][i][l]);
+    if (dbeta) atomicAdd(dbeta + col, sacc[1][i][l]);
+    if (dbias) atomicAdd(dbias + col, sacc[2][i][l]);
+  }
+}
+
+static int g_ln_variant = 0;       // hamt_ln_set_variant: 0 = ln_bwd_kernel (default), 1 / 2 = ln_bwd_kernel_v2 with 1 / 2 CTAs per SM, 3 = ln_bwd_kernel_v3 (all experimental)
 void ln_set_variant(int v) { g_ln_variant = v; }
 
 static int grid_for_rows(int M, int wpb, int max_ctas) {
@@ -295,6 +375,12 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
   const int grid = grid_for_rows(M, 8 * 4, 148 * 2);
   auto DY = (const __nv_bfloat16*)dy; auto Z = (const __nv_bfloat16*)z; auto DRI = (const __nv_bfloat16*)dres_in;
   auto DX = (__nv_bfloat16*)dx; auto DR = (__nv_bfloat16*)dres;
+  if (g_ln_variant == 3) {
+    if (H == 768) launch_pdl(ln_bwd_kernel_v3<3>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    else if (H == 512) launch_pdl(ln_bwd_kernel_v3<2>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    else launch_pdl(ln_bwd_kernel_v3<4>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    return check_launch("ln_bwd_kernel_v3");
+  }
   if (g_ln_variant == 1 || g_ln_variant == 2) {
 #define HAMT_LNV2(NCH_)                                                                                                        \
   {                                                                                                                            \
