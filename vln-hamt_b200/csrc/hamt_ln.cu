@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
 // scheduling changes aimed at the small-M launches (M = 2.5 k .. 8.5 k rows, 26 us at 1.2 TB/s -- 40 of the 44 launches per step):
 //   * the residual-path gradient row (dres_in) is requested together with dy and z instead of after the two warp reductions
 //     (one exposed HBM latency per row less);
-//   * the cross-warp accumulators live in shared memory as [3][NCH*8][32] (value index major, lane minor) so the 72 shared atomics of
-//     every lane hit 32 consecutive banks; the row-major [3][H] layout of ln_bwd_kernel gives 8-way bank conflicts (lane stride 32 B).
+//   * the cross-warp reduction at the end goes through warp-private shared slabs [warp][3][NCH*8][32] (value index major, lane minor:
+//     32 consecutive banks per store) that the CTA folds afterwards; ln_bwd_kernel uses 72 shared fp32 atomics per lane on a row-major
+//     [3][H] array -- 8-way bank conflicts, and every shared fp32 atomic is a compare-and-swap spin loop on sm_100 (ATOMS.CAST.SPIN).
 // OCC2: compile for two resident CTAs per SM (128 registers, some spills) instead of one (246 registers; the default kernel also needs
 // 238 and therefore runs 8 warps per SM) -- which of the two wins is a measurement for round 2.
 template <int NCH, bool OCC2>
@@ -195,12 +196,11 @@ __global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv
   pdl_grid_sync();
   constexpr int H = NCH * 256;
   constexpr int NV = NCH * 8;                 // values per lane
-  __shared__ float sacc[3][NV][32];
+  extern __shared__ float slab_all[];                 // [warps][3][NV][32]: warp-private, written once at the end (no atomics: fp32
+                                                      // shared-memory atomics are compare-and-swap loops on sm_100)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const DropState ds = drop_init(dc);
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&sacc[0][0][0])[i] = 0.f;
-  __syncthreads();
   float g[NV];
   load_vec_f32<NCH>(gamma, lane, g);
   float acc_g[NV], acc_b[NV], acc_x[NV];
@@ -250,26 +250,30 @@ __global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv
       store_row_bf16<NCH>(dx + (long long)row * H, lane, dz);
     }
   }
+  float* slab = slab_all + (threadIdx.x >> 5) * (3 * H) + lane;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    atomicAdd(&sacc[0][i][lane], acc_g[i]);
-    atomicAdd(&sacc[1][i][lane], acc_b[i]);
-    atomicAdd(&sacc[2][i][lane], acc_x[i]);
+    slab[(0 * NV + i) * 32] = acc_g[i];
+    slab[(1 * NV + i) * 32] = acc_b[i];
+    slab[(2 * NV + i) * 32] = acc_x[i];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
-    const int i = idx >> 5, l = idx & 31;                     // value i of lane l  ->  column (i / 8) * 256 + l * 8 + (i % 8)
+  for (int idx = threadIdx.x; idx < 3 * H; idx += blockDim.x) {       // fold the warp-private slabs, one global red per column and CTA
+    float v = slab_all[idx];
+    for (int w = 1; w < wpb; ++w) v += slab_all[w * 3 * H + idx];
+    const int a = idx / H, r = idx % H;
+    const int i = r >> 5, l = r & 31;                         // value i of lane l  ->  column (i / 8) * 256 + l * 8 + (i % 8)
     const int col = (i >> 3) * 256 + l * 8 + (i & 7);
-    if (dgamma) atomicAdd(dgamma + col, sacc[0][i][l]);
-    if (dbeta) atomicAdd(dbeta + col, sacc[1][i][l]);
-    if (dbias) atomicAdd(dbias + col, sacc[2][i][l]);
+    float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
+    if (dst) atomicAdd(dst + col, v);
   }
 }
 
 // EXPERIMENTAL variant 3: as v2, but the three column-sum accumulators are not kept in registers across rows (72 registers per lane,
-// the reason the kernels above need ~240 registers and run one CTA = 8 warps per SM): every row adds its 72 contributions per lane
-// straight into the conflict-free shared layout with shared-memory atomics (32 consecutive banks per instruction).  Aim: <= 128
-// registers without spills -> 2 CTAs per SM, twice the loads in flight.
+// the reason the kernels above need ~240 registers and run one CTA = 8 warps per SM).  Every warp owns a private [3][NCH*8][32] slab
+// in dynamic shared memory (lane-minor: 32 consecutive banks per access, no other warp touches it) and adds its row's contributions
+// with plain load / add / store -- fp32 shared-memory atomics compile to a compare-and-swap spin loop on sm_100 (ATOMS.CAST.SPIN), so
+// they are avoided.  The slabs are folded by the CTA at the end.  Aim: <= 128 registers without spills -> 2 CTAs per SM.
 template <int NCH>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -279,12 +283,13 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* 
   pdl_grid_sync();
   constexpr int H = NCH * 256;
   constexpr int NV = NCH * 8;
-  __shared__ float sacc[3][NV][32];
+  extern __shared__ float slab_all[];                 // [warps][3][NV][32]
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const DropState ds = drop_init(dc);
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&sacc[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < wpb * 3 * H; i += blockDim.x) slab_all[i] = 0.f;
   __syncthreads();
+  float* slab = slab_all + (threadIdx.x >> 5) * (3 * H) + lane;      // element (a, i) of this lane: slab[(a * NV + i) * 32]
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float d[NV], zz[NV], o[NV];
     load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
@@ -303,8 +308,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* 
         const int i = c * 8 + j;
         const float xh = (zz[i] - mean) * rstd;
         const float gd = d[i] * gg[j];
-        atomicAdd(&sacc[0][i][lane], d[i] * xh);
-        atomicAdd(&sacc[1][i][lane], d[i]);
+        slab[(0 * NV + i) * 32] += d[i] * xh;
+        slab[(1 * NV + i) * 32] += d[i];
         s1 += gd;
         s2 += gd * xh;
         zz[i] = xh;
@@ -332,17 +337,19 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* 
           for (int j = 0; j < 8; ++j) d[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
       }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) atomicAdd(&sacc[2][i][lane], d[i]);
+      for (int i = 0; i < NV; ++i) slab[(2 * NV + i) * 32] += d[i];
       store_row_bf16<NCH>(dx + (long long)row * H, lane, d);
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < H; idx += blockDim.x) {
-    const int i = idx >> 5, l = idx & 31;
+  for (int idx = threadIdx.x; idx < 3 * H; idx += blockDim.x) {       // fold the warp-private slabs, one global red per column and CTA
+    float v = slab_all[idx];
+    for (int w = 1; w < wpb; ++w) v += slab_all[w * 3 * H + idx];
+    const int a = idx / H, r = idx % H;
+    const int i = r >> 5, l = r & 31;
     const int col = (i >> 3) * 256 + l * 8 + (i & 7);
-    if (dgamma) atomicAdd(dgamma + col, sacc[0][i][l]);
-    if (dbeta) atomicAdd(dbeta + col, sacc[1][i][l]);
-    if (dbias) atomicAdd(dbias + col, sacc[2][i][l]);
+    float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
+    if (dst) atomicAdd(dst + col, v);
   }
 }
 
@@ -376,16 +383,32 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
   auto DY = (const __nv_bfloat16*)dy; auto Z = (const __nv_bfloat16*)z; auto DRI = (const __nv_bfloat16*)dres_in;
   auto DX = (__nv_bfloat16*)dx; auto DR = (__nv_bfloat16*)dres;
   if (g_ln_variant == 3) {
-    if (H == 768) launch_pdl(ln_bwd_kernel_v3<3>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-    else if (H == 512) launch_pdl(ln_bwd_kernel_v3<2>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-    else launch_pdl(ln_bwd_kernel_v3<4>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    const size_t smem = (size_t)8 * 3 * H * sizeof(float);           // 8 warps x [3][H] fp32: 72 KB at H = 768
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 512 * 4);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4);
+      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+      attr_set = true;
+    }
+    if (H == 768) launch_pdl(ln_bwd_kernel_v3<3>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    else if (H == 512) launch_pdl(ln_bwd_kernel_v3<2>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+    else launch_pdl(ln_bwd_kernel_v3<4>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
     return check_launch("ln_bwd_kernel_v3");
   }
   if (g_ln_variant == 1 || g_ln_variant == 2) {
+    const size_t smem2 = (size_t)8 * 3 * H * sizeof(float);
 #define HAMT_LNV2(NCH_)                                                                                                        \
   {                                                                                                                            \
-    if (g_ln_variant == 2) launch_pdl(ln_bwd_kernel_v2<NCH_, true>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc); \
-    else launch_pdl(ln_bwd_kernel_v2<NCH_, false>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);                  \
+    static bool set_ = false;                                                                                                  \
+    if (!set_) {                                                                                                               \
+      cudaFuncSetAttribute(ln_bwd_kernel_v2<NCH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * NCH_ * 256 * 4); \
+      cudaFuncSetAttribute(ln_bwd_kernel_v2<NCH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * NCH_ * 256 * 4);\
+      set_ = true;                                                                                                             \
+    }                                                                                                                          \
+    if (g_ln_variant == 2) launch_pdl(ln_bwd_kernel_v2<NCH_, true>, grid, 256, smem2, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc); \
+    else launch_pdl(ln_bwd_kernel_v2<NCH_, false>, grid, 256, smem2, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);                  \
   }
     if (H == 768) HAMT_LNV2(3) else if (H == 512) HAMT_LNV2(2) else HAMT_LNV2(4)
 #undef HAMT_LNV2
