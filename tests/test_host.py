@@ -166,3 +166,52 @@ def test_packed_batch_layout_roundtrip_on_cpu():
             if v is None:
                 assert again[k] is None
         assert graph._signature(task, again) == graph._signature(task, b)
+
+
+def test_optimizer_host_side_grouping_and_validation():
+    """optim.build_optimizer groups parameters exactly like the reference's build_optimizer (pretrain_src/optim/misc.py:12-37); the
+    constructor validates like adamw.py:42-49; segment tables cover every parameter of the arena exactly once.  (Host logic only:
+    step() launches kernels and is covered by the GPU tests.)"""
+    from types import SimpleNamespace
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import optim
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    model = MultiStepNavCMTPreTraining(HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1, vocab_size=512))
+    opts = SimpleNamespace(optim="adamw", learning_rate=5e-5, betas=[0.9, 0.98], weight_decay=0.01, warmup_steps=10, num_train_steps=100)
+    opt = optim.build_optimizer(model, opts)
+    names = {id(p): n for n, p in model.named_parameters()}
+    decay = {names[id(p)] for p in opt.param_groups[0]["params"]}
+    no_decay = {names[id(p)] for p in opt.param_groups[1]["params"]}
+    assert decay | no_decay == set(names.values()) and not (decay & no_decay)
+    assert all(("bias" in n or "LayerNorm.weight" in n) for n in no_decay)
+    assert "bert.encoder.layer.0.output.LayerNorm.weight" in no_decay and "bert.encoder.layer.0.output.dense.weight" in decay
+    # 'layer_norm.weight' of the embedders does NOT match the reference's substring rule ('LayerNorm.weight') -> decayed, as in the reference
+    assert "bert.img_embeddings.layer_norm.weight" in decay
+    if os.path.isdir("/root/reference/pretrain_src/optim"):
+        sys.path.insert(0, "/root/reference/pretrain_src")
+        try:
+            from optim.misc import build_optimizer as ref_build
+        finally:
+            sys.path.pop(0)
+        ref = ref_build(model, opts)
+        assert {names[id(p)] for p in ref.param_groups[0]["params"]} == decay
+        assert {names[id(p)] for p in ref.param_groups[1]["params"]} == no_decay
+        assert ref.param_groups[0]["weight_decay"] == 0.01 and ref.param_groups[1]["weight_decay"] == 0.0
+    arena = model.arena()
+    cover = torch.zeros(arena.flat_param.numel() // 64, dtype=torch.int32)
+    for p in arena.params:
+        o = arena.offsets[id(p)]
+        cover[o // 64:(o + p.numel() + 63) // 64] += 1
+    assert int(cover.max()) == 1
+    assert torch.equal(opt.chunk_seg >= 0, cover == 1)
+    assert opt.seg_end.tolist() == [arena.offsets[id(p)] + p.numel() for p in opt.seg_params]
+    assert int(opt._active().sum()) == 0                                   # no gradients yet -> nothing would be updated
+    arena.grad(model.next_action.net[0].weight)
+    assert int(opt._active().sum()) == 1
+    opt.set_lr(optim.get_lr_sched(5, opts))
+    assert opt.param_groups[0]["lr"] == opt.param_groups[1]["lr"] == pytest.approx(2.5e-5)
+    with pytest.raises(ValueError, match="Invalid beta"):
+        optim.AdamW(arena, list(model.parameters()), betas=(1.0, 0.9))
+    with pytest.raises(ValueError, match="invalid optimizer"):
+        optim.build_optimizer(model, SimpleNamespace(optim="rangerlars", learning_rate=1e-4, betas=[0.9, 0.98], weight_decay=0.0))
