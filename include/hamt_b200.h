@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HAMT_ABI_VERSION 1
+#define HAMT_ABI_VERSION 2
 
 int hamt_abi_version(void);
 const char* hamt_last_error(void);
@@ -51,14 +51,16 @@ int hamt_gemm_set_auto_pair(int on);
  * Data-parallel runs set 148 - R during the backward pass so that the R CTAs of the NCCL all-reduce kernel that overlaps it (dp.py;
  * the reference overlaps its DDP buckets the same way, utils/misc.py:52-65) find free SMs instead of waiting for a GEMM to retire. */
 int hamt_gemm_set_sm_limit(int n);
-/* EXPERIMENTAL (default off, unmeasured): 16 epilogue warps on 32-column half groups for the ALU-bound GELU / dGELU / accumulate epilogues of
- * fully aligned 256-wide tiles (hamt_gemm.cu: epilogue_wide).  Results are identical to the default epilogue. */
+/* 16-warp epilogue for the ALU-bound dGELU dgrad (BertOutput backward: acc * gelu'(pre) + fused bias column sums) on fully aligned
+ * 256-wide tiles (hamt_gemm.cu: epilogue_wide): 270 -> 183 us at M = 34 560 (profiles/r02_kbench_variants.txt).  On by default; 0 selects
+ * the 8-warp epilogue (bit-identical results, kept for A/B measurements).  The same wide epilogue LOST on the store / GELU / accumulate
+ * epilogues (157 -> 167 us for GELU) and is not instantiated for them. */
 int hamt_gemm_set_wide_epilogue(int on);
 
 /* y = LayerNorm(dropout(x) + res) ; BertSelfOutput / BertOutput tail (vilmodel.py:139-143,181-185).
  * z_out (may alias x, may be null) receives dropout(x)+res in bf16; mean/rstd fp32 [M] (may be null). */
-int hamt_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd, int M,
-                int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+int hamt_ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
+                float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
 /* backward: dx (grad of x, dropout applied; null to skip), dres = dz + dres_in (null to skip); dgamma/dbeta/dbias
  * (column sums, fp32) are ACCUMULATED into; any may be null. */
 int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
@@ -107,10 +109,6 @@ typedef struct {
 int hamt_embed_feat_fwd(const hamt_embed_feat_desc* d, void* stream);
 int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_grads* g, void* stream);
 
-/* EXPERIMENTAL (default 0, unmeasured): 1 / 2 select ln_bwd_kernel_v2 (residual-gradient row prefetched with dy / z, bank-conflict-free
- * shared accumulators; compiled for 1 / 2 resident CTAs per SM), 3 selects ln_bwd_kernel_v3 (column sums accumulated in shared memory
- * every row instead of in 72 registers per lane) -- same arithmetic as the default kernel. */
-int hamt_ln_set_variant(int v);
 
 /* streaming helpers */
 int hamt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);

@@ -174,7 +174,9 @@ def self_output(sd: State, prefix: str, hidden: Tensor, residual: Tensor, rg: Re
     """BertSelfOutput / BertOutput: LN(dropout(dense(h)) + residual); vilmodel.py:139-143,181-185."""
     t = linear(sd, prefix + ".dense", hidden, rg)
     t = _hidden_drop(t, dp)
-    return rg.q(layer_norm(sd, prefix + ".LayerNorm", t + residual))
+    # bf16 regime: the CUDA path keeps the LayerNorm output in fp32 for the next residual add (the residual stream) and hands a
+    # bf16 copy to the GEMMs -- `linear` rounds its input itself, so the value returned here stays un-rounded
+    return layer_norm(sd, prefix + ".LayerNorm", t + residual)
 
 
 def bert_self_attention(sd: State, prefix: str, x: Tensor, add_mask: Tensor, n_heads: int, rg: Regime,
@@ -281,7 +283,7 @@ def pano_encode(sd: State, prefix: str, pano_img: Tensor, pano_ang: Tensor, n_la
     zero_mask = torch.zeros(N, 1, 1, P, device=e.device)
     for l in range(n_layers):
         e = bert_layer(sd, f"{prefix}.pano_encoder.layer.{l}", e, zero_mask, n_heads, rg, dp)
-    return e.mean(dim=1)
+    return rg.q(e).mean(dim=1)          # the mean-pool kernel reads the bf16 copy
 
 
 def history_embeddings(sd: State, cfg, prefix: str, img: Optional[Tensor], ang: Optional[Tensor],
@@ -333,6 +335,7 @@ def encoder(sd: State, cfg, prefix: str, txt: Tensor, txt_mask: Tensor, hist: Te
         visn, visn_mask = torch.cat([hist, ob], 1), torch.cat([hist_mask, ob_mask], -1)
     for l in range(cfg.num_x_layers):
         txt, visn = lxrt_x_layer(sd, f"{prefix}.x_layers.{l}", txt, txt_mask, visn, visn_mask, nh, rg, dp)
+    txt, visn = rg.q(txt), rg.q(visn)   # what the backbone hands to the heads is the bf16 copy
     hist = visn[:, :T1]
     ob_out = visn[:, T1:] if ob is not None else None
     return txt, hist, ob_out
@@ -428,7 +431,7 @@ def backbone_itm(sd: State, cfg, txt_ids, txt_masks, hist_img, hist_ang, hist_pa
     visn_mask = torch.cat([hist_mask] + neg_masks, 0)
     for l in range(cfg.num_x_layers):
         txt, visn = lxrt_x_layer(sd, f"{prefix}.encoder.x_layers.{l}", txt, txt_mask_r, visn, visn_mask, nh, rg, dp)
-    fused = txt[:, 0] * visn[:, 0]
+    fused = rg.q(txt[:, 0]) * rg.q(visn[:, 0])
     return torch.stack(torch.split(fused, B), 1)
 
 
@@ -533,13 +536,13 @@ def navcmt_language(sd: State, cfg, txt_ids, txt_masks, rg: Regime = FP32, dp: O
     if cfg.fix_lang_embedding:
         txt = txt.detach()
     if cfg.no_lang_ca:
-        outs = [txt]
+        outs = [rg.q(txt)]
         for l in range(cfg.num_x_layers):
             p = f"encoder.x_layers.{l}"
             a = bert_self_attention(sd, p + ".lang_self_att", txt, m, nh, rg, dp)
-            outs.append(ffn(sd, p + ".lang_inter", p + ".lang_output", a, rg, dp))
+            outs.append(rg.q(ffn(sd, p + ".lang_inter", p + ".lang_output", a, rg, dp)))
         return outs
-    return txt
+    return rg.q(txt)                    # the mode returns the bf16 copy
 
 
 def navcmt_history(sd: State, cfg, hist_img, hist_ang, ob_step_ids, pano_img=None, pano_ang=None,
@@ -588,6 +591,7 @@ def navcmt_visual(sd: State, cfg, txt_embeds, txt_masks, hist_embeds, hist_masks
             txt = all_txt[l]
         txt, visn = lxrt_x_layer(sd, f"encoder.x_layers.{l}", txt, txt_mask, visn, visn_mask, nh, rg, dp,
                                  no_lang_ca=cfg.no_lang_ca)
+    txt, visn = rg.q(txt), rg.q(visn)
     hist, ob = visn[:, :T1], visn[:, T1:]
     if cfg.no_lang_ca or cfg.act_pred_token == "ob":
         fused = ob

@@ -5,7 +5,11 @@ container where /root/reference exists):
 
 For each proxy task (and the finetune NavCMT modes) the reference model is built from
 pretrain_src/config/r2r_model_config.json, loaded with the deterministic ``seeded_state_dict``
-(vln-hamt_b200/synth.py), run in eval mode on ``make_batch`` inputs, and its outputs are stored.
+(vln-hamt_b200/synth.py), run in eval mode on ``make_batch`` inputs, and its outputs are stored --
+once in fp32 (the reference's own arithmetic) and once under ``torch.autocast(bfloat16)``
+(``*_autocast`` keys): the distance between the two is the reference's OWN bf16 error on these
+inputs and is the yardstick of the model-level parity tests (|ours - fp32| <= 1.5 x |autocast - fp32|).
+The ``full_b64`` case is the headline benchmark shape (batch 64, ITM 32, txt 80, hist 15 x 36, obs 37).
 Everything is regenerated from seeds on the test machine, so the fixtures only hold outputs (a few
 hundred KB).  TEST INFRASTRUCTURE ONLY.
 """
@@ -32,15 +36,27 @@ CASES = [
     ("full_b2", dict(), dict(batch_size=2, txt_len=80, hist_len=15)),
     ("full_ragged_b3", dict(), dict(batch_size=3, txt_len=40, hist_len=6, ragged=True)),
     ("small_l2x1_b4", dict(num_l_layers=2, num_x_layers=1, num_h_pano_layers=1), dict(batch_size=4, txt_len=24, hist_len=5, ragged=True)),
+    ("full_b64", dict(), dict(batch_size=64, txt_len=80, hist_len=15)),
 ]
 WEIGHT_SEED, BATCH_SEED, RNG_SEED = 11, 7, 5
 
 
-def compact(task, out):
-    """Keep fixtures small: the MLM logits are stored as a column slice + row statistics."""
+def compact(task, out, big=False):
+    """Keep fixtures small: the MLM logits are stored as a column slice + row statistics (64 columns in the batch-64 case,
+    whose MRC logits / targets are also cut to 64 columns)."""
     if task == "mlm" and out.dim() == 2 and out.shape[1] > 4096:
-        return dict(head=out[:, :256].clone(), lse=torch.logsumexp(out, 1), argmax=out.argmax(1), mean=out.mean(1))
-    return out.clone()
+        out = out.float()
+        return dict(head=out[:, :64 if big else 256].clone(), lse=torch.logsumexp(out, 1), argmax=out.argmax(1), mean=out.mean(1))
+    if big and task == "mrc" and out.dim() == 2 and out.shape[1] > 64:
+        return out[:, :64].float().clone()
+    return out.float().clone() if out.is_floating_point() else out.clone()
+
+
+def batch_kwargs(task, bkw):
+    """ITM runs at half the batch (pretrain_src/data/loader.py:130) in the batch-64 case."""
+    if bkw["batch_size"] >= 64 and task == "itm":
+        return dict(bkw, batch_size=bkw["batch_size"] // 2)
+    return bkw
 
 
 def main():
@@ -55,17 +71,19 @@ def main():
         sd = synth.seeded_state_dict(ours, seed=WEIGHT_SEED)
         model.load_state_dict(sd)
         rec = {"meta": dict(case=name, cfg=cfg_over, batch=bkw, weight_seed=WEIGHT_SEED, batch_seed=BATCH_SEED, rng_seed=RNG_SEED)}
+        big = bkw["batch_size"] >= 64
         for task in TASKS:
-            b = synth.make_batch(task, seed=BATCH_SEED, **bkw)
+            b = synth.make_batch(task, seed=BATCH_SEED, **batch_kwargs(task, bkw))
             for cl in (False, True):
-                np.random.seed(RNG_SEED)
-                torch.manual_seed(RNG_SEED)
-                with torch.no_grad():
-                    out = model(b, task, compute_loss=cl)
-                outs = out if isinstance(out, tuple) else (out,)
-                rec[f"{task}_{'loss' if cl else 'logits'}"] = [compact(task, o) for o in outs]
+                for ac in (False, True):
+                    np.random.seed(RNG_SEED)
+                    torch.manual_seed(RNG_SEED)
+                    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16, enabled=ac):
+                        out = model(b, task, compute_loss=cl)
+                    outs = out if isinstance(out, tuple) else (out,)
+                    rec[f"{task}_{'loss' if cl else 'logits'}{'_autocast' if ac else ''}"] = [compact(task, o, big) for o in outs]
         torch.save(rec, os.path.join(GOLD, f"pretrain_{name}.pt"))
-        print("wrote", name, {k: [tuple(t.shape) if torch.is_tensor(t) else "dict" for t in v] for k, v in rec.items() if k != "meta"})
+        print("wrote", name, {k: [tuple(t.shape) if torch.is_tensor(t) else "dict" for t in v] for k, v in rec.items() if k != "meta" and not k.endswith("_autocast")})
 
     # finetune facade (NavCMT modes) on a reduced-depth model
     fcfg = dict(num_l_layers=2, num_x_layers=2, num_h_pano_layers=1, hist_enc_pano=True, no_lang_ca=False, act_pred_token="ob_txt",

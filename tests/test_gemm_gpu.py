@@ -8,6 +8,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _dgelu_ref(x):
+    return 0.5 * (1.0 + torch.erf(x * 0.7071067811865476)) + x * 0.3989422804014327 * torch.exp(-0.5 * x * x)
+
+
 def _ops():
     import hamt_b200  # noqa: F401
     from hamt_b200 import ops
@@ -191,39 +195,31 @@ def test_gemm_fused_colsum(M, N, K, tile_n):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("HAMT_TEST_EXPERIMENTAL"), reason="experimental 16-warp epilogue: opt-in (HAMT_TEST_EXPERIMENTAL=1), off by default in the product")
 @pytest.mark.parametrize("M,tile_n", [(1024, 256), (2048, 512)])
-def test_gemm_wide_epilogue_matches_default(M, tile_n):
-    """hamt_gemm_set_wide_epilogue(1): same math on 16 epilogue warps -> outputs bit-identical to the default epilogue for the four
-    bf16-store paths (store+bias, GELU + pre-activation, dGELU + column sums, accumulate)."""
+def test_gemm_wide_dgelu_epilogue_matches_8warp_epilogue(M, tile_n):
+    """The dGELU dgrad runs a 16-warp epilogue on aligned 256-wide tiles (default); hamt_gemm_set_wide_epilogue(0) selects the 8-warp
+    epilogue: same math -> bit-identical outputs, column sums equal up to fp32 summation order."""
     import hamt_b200  # noqa: F401
     from hamt_b200 import _lib
     ops = _ops()
     lib = _lib.load()
-    N, K = 768, 256
-    x, w, bias = _rand((M, K), 31), _rand((N, K), 32, 0.05), torch.randn(N, device="cuda")
+    N = 768
     dy, w2 = _rand((M, 512), 33), _rand((512, N), 34, 0.05)
     pre = _rand((M, N), 35)
 
     def run():
-        aux = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
-        o1 = ops.gemm(x, w, bias=bias, tile_n=tile_n)
-        o2 = ops.gemm(x, w, bias=bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=aux, tile_n=tile_n)
         cs = torch.zeros(N, device="cuda")
         o3 = ops.gemm(dy, w2, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=pre, colsum=cs, tile_n=tile_n)
-        o4 = pre.clone()
-        ops.gemm(dy, w2, b_mn=True, out=o4, accumulate=True, tile_n=tile_n)
         torch.cuda.synchronize()
-        return o1, o2, aux, o3, cs, o4
+        return o3, cs
 
-    base = run()
-    lib.hamt_gemm_set_wide_epilogue(1)
+    wide = run()
+    lib.hamt_gemm_set_wide_epilogue(0)
     try:
-        wide = run()
+        base = run()
     finally:
-        lib.hamt_gemm_set_wide_epilogue(0)
-    for i, (a, b) in enumerate(zip(base, wide)):
-        if i == 4:
-            assert (a - b).abs().max().item() <= 1e-3 * max(1.0, a.abs().max().item())
-        else:
-            assert torch.equal(a, b), i
+        lib.hamt_gemm_set_wide_epilogue(1)
+    assert torch.equal(base[0], wide[0])
+    assert (base[1] - wide[1]).abs().max().item() <= 1e-3 * max(1.0, base[1].abs().max().item())
+    ref = (dy.float() @ w2.float()) * _dgelu_ref(pre.float())
+    assert (wide[0].float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())

@@ -109,3 +109,39 @@ def test_packed_prefetch_matches_dict_batch(task):
         got.append(reader.pop())
     assert len(trainer.steps) == 1, "the packed batch must hit the same captured graph"
     assert np.allclose(got, want, rtol=0, atol=1e-6), (got, want)
+
+
+def test_graph_accumulate_and_capture_during_accumulation():
+    """gradient_accumulation_steps > 1 (main_r2r.py:243-249): `step(..., accumulate=True)` adds to the gradients instead of
+    resetting them, and a first-use capture in the middle of an accumulation (its warm-up passes run the model) leaves the
+    already accumulated gradients intact."""
+    from hamt_b200 import graph, synth
+    model = _build()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    b = synth.make_batch("sap", batch_size=4, txt_len=24, hist_len=5, seed=1)
+    bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    model.zero_grad(set_to_none=True)
+    model(bd, "sap", compute_loss=True).mean().backward()          # micro-batch 1, eager
+    torch.cuda.synchronize()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    seed_before = int(model.arena().seed.item())
+    trainer = graph.GraphedTrainer(model)
+    trainer.step("sap", graph.add_sync_free_extras("sap", b), accumulate=True)     # micro-batch 2: captured on first use
+    torch.cuda.synchronize()
+    g2 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert set(g1) == set(g2)
+    for n in g1:
+        assert (g2[n] - 2 * g1[n]).abs().max().item() <= 3e-2 * g1[n].abs().max().item() + 1e-5, n
+    assert int(model.arena().seed.item()) != seed_before            # exactly the replay advanced it (warm-up passes did not) ...
+    trainer.step("sap", graph.add_sync_free_extras("sap", b), accumulate=True)
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - 3 * g1[n]).abs().max().item() <= 4e-2 * g1[n].abs().max().item() + 1e-5, n
+    trainer.step("sap", graph.add_sync_free_extras("sap", b))       # default: a fresh accumulation
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - g1[n]).abs().max().item() <= 2e-2 * g1[n].abs().max().item() + 1e-5, n

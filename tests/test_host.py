@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     import hamt_b200  # noqa: F401
     from hamt_b200 import _lib
     lib = _lib.load()
-    assert lib.hamt_abi_version() == 1
+    assert lib.hamt_abi_version() == 2
     decl = set(re.findall(r"\b(hamt_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", "hamt_b200.h")).read()))
     assert len(decl) >= 24
     for name in sorted(decl):
@@ -41,7 +41,7 @@ def test_invalid_arguments_are_reported_not_crashing():
     lib = _lib.load()
     assert lib.hamt_gemm_bf16(None, 0, 0, None, 0, 0, None, 0, 0, 0, 0, 0, 0, None, 0, 0, None, 0, 1.0, 0, 0, None, None) != 0
     assert "empty" in _lib.last_error()
-    assert lib.hamt_ln_fwd(None, None, None, None, None, None, None, None, 4, 100, 1e-12, None, 0, 0.0, None) != 0
+    assert lib.hamt_ln_fwd(None, None, None, None, None, None, None, None, None, None, 4, 100, 1e-12, None, 0, 0.0, None) != 0
     assert "hidden size" in _lib.last_error()
     assert lib.hamt_rowdot_fwd(None, None, None, None, 4, 9, 768, None) != 0
 

@@ -6,14 +6,14 @@ Comparators
 
 What can and cannot be asserted (measured, see DESIGN.md "Parity"): a 13..15-layer bf16 pipeline is chaotic at the rounding
 level -- perturbing the weights by 1e-7 relative moves the bf16-regime logits by ~1.8e-2, the same size as the bf16-vs-fp32 gap
-(tests/test_oracle.py::test_bf16_regime_rounding_chaos).  The reference's own torch.autocast(bf16) run differs from its fp32 run by
-1.2e-2 (SAP) .. 3e-2 (MLM).  So "< 1e-3 in bf16" is asserted where it is attainable -- per kernel (tests/test_*_gpu.py) -- and
-at model level the assertions are:
-   * logits:  |ours - reference_fp32| <= TOL_LOGITS, and not worse than RATIO x the bf16-regime oracle's own distance to fp32;
+(tests/test_oracle.py::test_bf16_regime_rounding_chaos).  The reference's OWN torch.autocast(bf16) run differs from its fp32 run by
+0.6e-2 .. 1.7e-2 on these inputs; those outputs are stored next to the fp32 ones in the goldens (`*_autocast`) and are the yardstick:
+   * logits:  |ours - reference_fp32| <= RATIO (1.5) x |reference_autocast - reference_fp32|, per task and case (max-abs), and
+              <= TOL_LOGITS absolutely;
    * losses:  |ours - reference_fp32| <= TOL_LOSS * max(1, |ref|);
-   * SAP / finetune action argmax bit-exact wherever the reference's top-2 margin exceeds 2 x TOL_LOGITS, and always equal to
-     the reference when the margin is that large;
+   * SAP / finetune action argmax bit-exact on every row whose reference top-2 margin exceeds twice the measured error;
    * -inf patterns (masked_fill_(nav_type == 0)) identical;  integer outputs bit-exact.
+"< 1e-3 in bf16" is asserted where it is attainable: per kernel (tests/test_*_gpu.py).
 """
 import os
 
@@ -25,9 +25,9 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TASKS = ("mlm", "sap", "sar", "sprel", "mrc", "itm")
-TOL_LOGITS = 4e-2     # max-abs, logits (std 0.3 .. 0.55) vs the fp32 reference; measured 0.8e-2 .. 2.4e-2
+TOL_LOGITS = 3e-2     # absolute ceiling, max-abs, logits (std 0.3 .. 0.55) vs the fp32 reference
 TOL_LOSS = 1e-1       # un-reduced loss entries (MSE on angles amplifies a logit error by 2|pred - target| <= 2 pi)
-RATIO = 3.0           # ours may be at most this many times further from fp32 than the bf16-regime oracle (+ 5e-3 slack)
+RATIO = 1.5           # ours may be at most this many times further from fp32 than the reference's own torch.autocast(bf16) run
 
 
 def _build(cfg_over, weight_seed, device="cuda"):
@@ -53,67 +53,153 @@ def _err(got, want):
     return (got[fin] - want[fin]).abs().max().item() if fin.any() else 0.0
 
 
-def _mlm_compact(out):
-    return dict(head=out[:, :256], lse=torch.logsumexp(out.float(), 1), argmax=out.argmax(1), mean=out.float().mean(1))
+def _comparable(task, out, gold):
+    """Bring an output into the (possibly compacted) form its golden counterpart was stored in (oracle/make_golden.py compact())."""
+    if isinstance(gold, dict):                  # MLM logits: column slice + row statistics
+        return out[:, :gold["head"].shape[1]], gold["head"]
+    if out.dim() == 2 and gold.dim() == 2 and out.shape[1] > gold.shape[1]:      # batch-64 MRC: 64 columns
+        return out[:, :gold.shape[1]], gold
+    return out, gold
+
+
+def _batch_kwargs(task, bkw):
+    return dict(bkw, batch_size=bkw["batch_size"] // 2) if (bkw["batch_size"] >= 64 and task == "itm") else bkw
+
+
+def _check_case_against_goldens(case, rec, run_model, report, failures, with_oracle=None):
+    """Shared by the eval-mode cases: every task, logits and un-reduced losses, against the fp32 goldens with the reference's own
+    autocast(bf16) distance as the yardstick."""
+    from hamt_b200 import synth
+    meta = rec["meta"]
+    for task in TASKS:
+        b = synth.make_batch(task, seed=meta["batch_seed"], **_batch_kwargs(task, meta["batch"]))
+        for cl in (False, True):
+            np.random.seed(meta["rng_seed"]); torch.manual_seed(meta["rng_seed"])
+            out = run_model(b, task, cl)
+            outs = list(out) if isinstance(out, tuple) else [out]
+            o16 = with_oracle(b, task, cl) if with_oracle is not None else None
+            kind = "loss" if cl else "logits"
+            gold, gold_ac = rec[f"{task}_{kind}"], rec[f"{task}_{kind}_autocast"]
+            for i, (g_ours, g_ref, g_ac) in enumerate(zip(outs, gold, gold_ac)):
+                key = f"{case}/{task}/{kind}[{i}]"
+                g_ours, g_ref_t = _comparable(task, g_ours, g_ref)
+                g_ac = g_ac["head"] if isinstance(g_ac, dict) else g_ac
+                if g_ref_t.dtype in (torch.int64, torch.bool):
+                    assert torch.equal(g_ours.cpu(), g_ref_t), key
+                    continue
+                e_ref, e_ac = _err(g_ours, g_ref_t), _err(g_ac, g_ref_t)
+                line = f"{key}: ours_vs_reference_fp32={e_ref:.3e} reference_autocast_vs_fp32={e_ac:.3e} ratio={e_ref / max(e_ac, 1e-12):.2f}"
+                if o16 is not None:
+                    g_o = _comparable(task, o16[i], g_ref)[0]
+                    line += f" bf16oracle_vs_reference_fp32={_err(g_o, g_ref_t):.3e} ours_vs_bf16oracle={_err(g_ours, g_o):.3e}"
+                report.append(line)
+                if cl:
+                    tol = TOL_LOSS * max(1.0, g_ref_t[torch.isfinite(g_ref_t)].abs().max().item())
+                    if e_ref > tol:
+                        failures.append(f"{key}: |ours - reference| = {e_ref:.3e} > {tol:.3e}")
+                else:
+                    if e_ref > TOL_LOGITS:
+                        failures.append(f"{key}: |ours - reference| = {e_ref:.3e} > {TOL_LOGITS:.1e}")
+                    if e_ref > RATIO * e_ac + 1e-6:
+                        failures.append(f"{key}: ours is {e_ref:.3e} from the fp32 reference, the reference's own autocast(bf16) run {e_ac:.3e} "
+                                        f"(ratio {e_ref / max(e_ac, 1e-12):.2f} > {RATIO})")
+            if task == "sap" and not cl:
+                ours_l, ref_l = outs[0].float().cpu(), gold[0]
+                e_sap = _err(ours_l, ref_l)
+                top2 = ref_l.topk(2, dim=1).values
+                margin_ok = (top2[:, 0] - top2[:, 1]) > 2 * e_sap
+                report.append(f"{case}/sap argmax: rows={ref_l.shape[0]} checked={int(margin_ok.sum())} (margin > 2 x {e_sap:.3e}) "
+                              f"equal={int((ours_l.argmax(1) == ref_l.argmax(1)).sum())}")
+                if not torch.equal(ours_l.argmax(1)[margin_ok], ref_l.argmax(1)[margin_ok]):
+                    failures.append("SAP argmax actions differ from the reference")
+                if int(margin_ok.sum()) < (ref_l.shape[0] * 3) // 4:
+                    failures.append(f"SAP argmax: only {int(margin_ok.sum())} of {ref_l.shape[0]} rows have a margin above twice the measured error")
 
 
 @pytest.mark.parametrize("case", ["small_l2x1_b4", "full_ragged_b3", "full_b2"])
 def test_pretrain_tasks_vs_reference_golden_and_oracle(case):
-    from hamt_b200 import synth
     from oracle import hamt_oracle as O
     rec = torch.load(os.path.join(GOLD, f"pretrain_{case}.pt"))
     meta = rec["meta"]
     cfg, model, sd = _build(meta["cfg"], meta["weight_seed"])
     model.eval()
+
+    def run_model(b, task, cl):
+        with torch.no_grad():
+            return model(_to_dev(b), task, compute_loss=cl)
+
+    def run_oracle(b, task, cl):
+        np.random.seed(meta["rng_seed"]); torch.manual_seed(meta["rng_seed"])
+        with torch.no_grad():
+            o = O.pretrain_forward(sd, cfg, b, task, compute_loss=cl, rg=O.BF16)
+        return list(o) if isinstance(o, tuple) else [o]
+
     report, failures = [], []
-    for task in TASKS:
-        b = synth.make_batch(task, seed=meta["batch_seed"], **meta["batch"])
-        bd = _to_dev(b)
-        for cl in (False, True):
-            np.random.seed(meta["rng_seed"]); torch.manual_seed(meta["rng_seed"])
-            with torch.no_grad():
-                out = model(bd, task, compute_loss=cl)
-            outs = list(out) if isinstance(out, tuple) else [out]
-            np.random.seed(meta["rng_seed"]); torch.manual_seed(meta["rng_seed"])
-            with torch.no_grad():
-                o16 = O.pretrain_forward(sd, cfg, b, task, compute_loss=cl, rg=O.BF16)
-            o16 = list(o16) if isinstance(o16, tuple) else [o16]
-            gold = rec[f"{task}_{'loss' if cl else 'logits'}"]
-            for i, (g_ours, g_o16, g_ref) in enumerate(zip(outs, o16, gold)):
-                key = f"{case}/{task}/{'loss' if cl else 'logits'}[{i}]"
-                if isinstance(g_ref, dict):     # compacted MLM logits: column slice + row statistics
-                    g_ours, g_o16, g_ref = _mlm_compact(g_ours)["head"], _mlm_compact(g_o16)["head"], g_ref["head"]
-                if g_ref.dtype in (torch.int64, torch.bool):
-                    assert torch.equal(g_ours.cpu(), g_ref), key
-                    continue
-                e_ref, e_o16_ref, e_o16 = _err(g_ours, g_ref), _err(g_o16, g_ref), _err(g_ours, g_o16)
-                report.append(f"{key}: ours_vs_reference_fp32={e_ref:.3e} bf16oracle_vs_reference_fp32={e_o16_ref:.3e} ours_vs_bf16oracle={e_o16:.3e}")
-                tol = TOL_LOSS * max(1.0, g_ref[torch.isfinite(g_ref)].abs().max().item()) if cl else TOL_LOGITS
-                if e_ref > tol:
-                    failures.append(f"{key}: |ours - reference| = {e_ref:.3e} > {tol:.3e}")
-                if not cl and e_ref > RATIO * e_o16_ref + 5e-3:
-                    failures.append(f"{key}: ours is {e_ref:.3e} from fp32 but the bf16-regime oracle only {e_o16_ref:.3e}")
-            if task == "sap" and not cl:
-                ours_l, ref_l = outs[0].float().cpu(), gold[0]
-                top2 = ref_l.topk(2, dim=1).values
-                margin_ok = (top2[:, 0] - top2[:, 1]) > 2 * TOL_LOGITS
-                report.append(f"{case}/sap argmax: ours={ours_l.argmax(1).tolist()} reference={ref_l.argmax(1).tolist()} checked={margin_ok.tolist()}")
-                if not torch.equal(ours_l.argmax(1)[margin_ok], ref_l.argmax(1)[margin_ok]):
-                    failures.append("SAP argmax actions differ from the reference")
+    _check_case_against_goldens(case, rec, run_model, report, failures, with_oracle=run_oracle)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/parity_{case}.txt", "w") as fh:
         fh.write("\n".join(report) + "\n")
     assert not failures, "\n".join(failures)
 
 
-def _proj_loss(out, seed):
-    """Well-conditioned scalar for gradient checks: fixed random projection of every finite output element."""
+def test_headline_batch64_vs_reference_golden_eager_and_graphed():
+    """BASELINE configs[1] shape (batch 64, ITM 32, txt 80, hist 15 x 36, obs 37, full depth): the cost model picks the CTA-pair /
+    split-K tiles the bench runs.  (1) eval-mode logits + losses of all six tasks against the goldens of the UNMODIFIED reference,
+    SAP argmax on all 64 rows with a sufficient margin; (2) the SAME captured-graph path the bench times (graph.GraphedTrainer,
+    train mode, dropout probabilities 0): the loss vector of every task against the reference's fp32 loss."""
+    from hamt_b200 import graph, synth
+    rec = torch.load(os.path.join(GOLD, "pretrain_full_b64.pt"))
+    meta = rec["meta"]
+    cfg, model, sd = _build(meta["cfg"], meta["weight_seed"])
+    model.eval()
+
+    def run_model(b, task, cl):
+        with torch.no_grad():
+            return model(_to_dev(b), task, compute_loss=cl)
+
+    report, failures = [], []
+    _check_case_against_goldens("full_b64", rec, run_model, report, failures)
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    trainer = graph.GraphedTrainer(model)
+    for task in TASKS:
+        b = synth.make_batch(task, seed=meta["batch_seed"], **_batch_kwargs(task, meta["batch"]))
+        np.random.seed(meta["rng_seed"]); torch.manual_seed(meta["rng_seed"])
+        bd = graph.add_sync_free_extras(task, b)
+        loss = trainer.step(task, _to_dev(bd)).detach().float().cpu()
+        torch.cuda.synchronize()
+        g_ref = rec[f"{task}_loss"][0]
+        e = _err(loss, g_ref)
+        tol = TOL_LOSS * max(1.0, g_ref.abs().max().item())
+        report.append(f"full_b64/{task}/graphed_loss: ours_vs_reference_fp32={e:.3e} (tol {tol:.2e}); mean ours={loss.mean():.5f} reference={g_ref.mean():.5f}")
+        if e > tol:
+            failures.append(f"full_b64/{task}: graphed loss differs from the reference by {e:.3e} > {tol:.3e}")
+        g = model.bert.encoder.x_layers[0].visual_attention.att.query.weight.grad
+        if g is None or not torch.isfinite(g).all() or float(g.abs().sum()) == 0.0:
+            failures.append(f"full_b64/{task}: the captured step left no finite gradient")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_full_b64.txt", "w") as fh:
+        fh.write("\n".join(report) + "\n")
+    assert not failures, "\n".join(failures)
+
+
+def _proj_loss(out, seed, positive=False):
+    """Well-conditioned scalar for gradient checks: fixed random projection of every finite output element.
+    positive: |w| instead of w.  The five ITM logits of a sample are near-identical functions of the text stream and of the shared
+    history CLS token (same instruction, slightly different trajectories), so a random-SIGN combination of them is a small difference
+    of large terms: the fp32 oracle's own gradient moves by 7.5 % when only its forward residual stream is rounded to bf16
+    (measured) -- an ill-conditioned comparator, not a property of the kernels.  Equal signs keep the sum
+    well conditioned; the cancelling case stays covered by mode 'loss' (cross-entropy over the same five logits)."""
     outs = list(out) if isinstance(out, tuple) else [out]
     total = 0.0
     for i, o in enumerate(outs):
         if not o.is_floating_point() or not o.requires_grad:
             continue
         w = torch.randn(o.shape, generator=torch.Generator().manual_seed(seed + i)).to(o.device)
+        if positive:
+            w = w.abs()
         fin = torch.isfinite(o)
         total = total + (torch.where(fin, o.float(), torch.zeros_like(o, dtype=torch.float32)) * w).sum() / max(1, int(fin.sum()))
     return total
@@ -138,7 +224,7 @@ def test_pretrain_gradients_vs_oracle(task, mode):
     cl = mode == "loss"
     np.random.seed(1); torch.manual_seed(1)
     out = model(_to_dev(b), task, compute_loss=cl)
-    loss = out.mean() if cl else _proj_loss(out, 100)
+    loss = out.mean() if cl else _proj_loss(out, 100, positive=task == "itm")
     loss.backward()
     torch.cuda.synchronize()
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -146,7 +232,7 @@ def test_pretrain_gradients_vs_oracle(task, mode):
         sdr["mlm_head.predictions.decoder.weight"] = sdr["bert.embeddings.word_embeddings.weight"]
     np.random.seed(1); torch.manual_seed(1)
     ref_out = O.pretrain_forward(sdr, cfg, b, task, compute_loss=cl, rg=O.BF16)
-    ref = ref_out.mean() if cl else _proj_loss(ref_out, 100)
+    ref = ref_out.mean() if cl else _proj_loss(ref_out, 100, positive=task == "itm")
     assert abs(float(loss) - float(ref)) < 1e-2 * max(1.0, abs(float(ref)))
     ref.backward()
     named = dict(model.named_parameters())

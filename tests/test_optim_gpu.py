@@ -111,3 +111,70 @@ def test_fused_adamw_on_model_gradients_vs_oracle():
         c = model(b, "sap", compute_loss=False).clone()
     fin = torch.isfinite(a)
     assert torch.equal(a[fin], c[fin])
+
+
+def test_optimizer_step_before_the_first_forward_and_checkpoint_roundtrip():
+    """the reference loop runs `optimizer.zero_grad(); optimizer.step()` BEFORE the first forward
+    (main_r2r.py:229-230).  No segment is active then and the bf16 weight shadow has never been cast: the step must not mark it
+    fresh (the first forward would read uninitialised GEMM operands).  Same hole: load_state_dict between a forward and the next
+    step.  Then `state_dict()` / `load_state_dict()` (utils/save.py:42) reproduce the trajectory."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import optim, synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    from types import SimpleNamespace
+    opts = SimpleNamespace(optim="adamw", learning_rate=5e-3, betas=[0.9, 0.98], weight_decay=0.01, warmup_steps=2, num_train_steps=10)
+
+    def fresh():
+        m = MultiStepNavCMTPreTraining(HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1))
+        m.load_state_dict(synth.seeded_state_dict(m, seed=3))
+        m = m.cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return m
+
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.make_batch("sap", batch_size=2, txt_len=16, hist_len=3, seed=1).items()}
+    ref_model = fresh()
+    want = ref_model(b, "sap", compute_loss=True).detach().clone()
+
+    model = fresh()
+    opt = optim.build_optimizer(model, opts)
+    model.arena().flat_bf16.fill_(float("nan"))          # what "uninitialised" may look like
+    opt.zero_grad()
+    opt.step(max_grad_norm=5.0, zero_grad=True)           # nothing active: a no-op on the weights
+    got = model(b, "sap", compute_loss=True)
+    assert torch.isfinite(got).all() and torch.equal(got.detach(), want)
+    # load_state_dict after a forward, then step (no grads), then forward: the new weights must be used
+    got.mean().backward()
+    opt.step(max_grad_norm=5.0, zero_grad=True)
+    sd2 = synth.seeded_state_dict(model, seed=4)
+    model.load_state_dict(sd2)
+    opt.step(max_grad_norm=5.0, zero_grad=True)           # no active segment; must not declare the stale shadow fresh
+    ref2 = fresh()
+    ref2.load_state_dict(sd2)
+    assert torch.equal(model(b, "sap", compute_loss=True).detach(), ref2(b, "sap", compute_loss=True).detach())
+
+    # ---- checkpoint round trip: two steps, save, one more step == load into a new optimizer, one more step
+    m1 = fresh()
+    o1 = optim.build_optimizer(m1, opts)
+    for step in range(2):
+        m1(b, "sap", compute_loss=True).mean().backward()
+        o1.set_lr(optim.get_lr_sched(step + 1, opts))
+        o1.step(max_grad_norm=5.0, zero_grad=True)
+    ck_model = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    ck_opt = o1.state_dict()
+    assert set(ck_opt) == {"state", "param_groups"} and len(ck_opt["param_groups"]) == 2
+    assert all(set(s) == {"step", "exp_avg", "exp_avg_sq"} and s["step"] == 2 for s in ck_opt["state"].values())
+    m1(b, "sap", compute_loss=True).mean().backward()
+    o1.set_lr(optim.get_lr_sched(3, opts))
+    o1.step(max_grad_norm=5.0, zero_grad=True)
+    m2 = fresh()
+    m2.load_state_dict(ck_model)
+    o2 = optim.build_optimizer(m2, opts)
+    o2.load_state_dict(ck_opt)
+    m2(b, "sap", compute_loss=True).mean().backward()
+    o2.set_lr(optim.get_lr_sched(3, opts))
+    o2.step(max_grad_norm=5.0, zero_grad=True)
+    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert (p - q).abs().max().item() <= 1e-6 * max(1.0, p.abs().max().item()), n

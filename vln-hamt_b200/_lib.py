@@ -42,7 +42,7 @@ SIGNATURES = {
     "hamt_gemm_set_auto_pair": [i32],
     "hamt_gemm_set_sm_limit": [i32],
     "hamt_gemm_set_wide_epilogue": [i32],
-    "hamt_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
+    "hamt_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
     "hamt_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, u32, f32, vp],
     "hamt_attn_fwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp],
     "hamt_attn_bwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, vp, ll, ll, vp, vp, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp, vp, vp, vp],
@@ -50,7 +50,6 @@ SIGNATURES = {
     "hamt_embed_text_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, u32, f32, vp],
     "hamt_embed_feat_fwd": [C.POINTER(EmbedFeatDesc), vp],
     "hamt_embed_feat_bwd": [C.POINTER(EmbedFeatDesc), C.POINTER(EmbedFeatGrads), vp],
-    "hamt_ln_set_variant": [i32],
     "hamt_cast_f32_to_bf16": [vp, vp, ll, vp],
     "hamt_colsum_bf16": [vp, ll, vp, i32, i32, vp],
     "hamt_mean_pool_fwd": [vp, vp, i32, i32, i32, vp],
@@ -84,7 +83,7 @@ def load():
         fn = getattr(lib, name)        # AttributeError if the .so does not export a declared symbol
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, i32)
-    if lib.hamt_abi_version() != 1:
+    if lib.hamt_abi_version() != 2:
         raise RuntimeError("hamt_b200: ABI version mismatch between _lib.py and libhamt_b200.so")
     _lib = lib
     return lib

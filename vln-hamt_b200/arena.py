@@ -38,6 +38,9 @@ class ParamArena:
         self.params: List[nn.Parameter] = []
         self._shadow_version = None
         self._fresh_version = None
+        self._shadow_valid = False          # True only after a FULL cast of flat_param into flat_bf16 (see shadow_is_fresh)
+        self._valid_version = None
+        self.external_prologue = False      # graph.py: the cast / gradient zeroing / seed advance run eagerly OUTSIDE the captured body
         self._touched: List[nn.Parameter] = []
         self._sentinel: Optional[nn.Parameter] = None
         self.anchor = None
@@ -83,6 +86,8 @@ class ParamArena:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_bf16 = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self._shadow_version = None
+        self._fresh_version = None
+        self._shadow_valid, self._valid_version = False, None     # flat_bf16 is uninitialised memory until the first full cast
         self._touched, self._sentinel = [], None
         self.anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)
         if self.seed is None or self.seed.device != dev:
@@ -100,22 +105,27 @@ class ParamArena:
             self.build()
 
     # ---------------------------------------------------------------- per-step protocol
-    def step_begin(self, training: bool):
-        """Call at the start of every model forward."""
+    def step_begin(self, training: bool, zero_grads: bool = True):
+        """Call at the start of every model forward (graph.py calls it eagerly before a replay and sets `external_prologue`
+        so that the captured body does not repeat it)."""
         if next(self.module.parameters()).device.type != "cuda":
             raise RuntimeError("hamt_b200: the compute path needs the model on a CUDA device (no CPU fallback)")
         self.ensure()
+        if self.external_prologue:
+            return
         # bf16 shadow refresh: ONE cast launch for every GEMM operand.  Training: every step (weights move every
         # optimizer step; in-place updates through `.data` bump no version counter, so this is unconditional --
-        # 1 GB of traffic, ~0.2 ms).  Eval: only when a parameter's version counter moved or after training.
-        ver = sum(p._version for p in self.params) if (not training or self._fresh_version is not None) else None
-        if training and self._fresh_version is not None and ver == self._fresh_version:
+        # 1 GB of traffic, ~0.2 ms) unless the fused optimizer refreshed a fully valid shadow in its own pass.
+        # Eval: only when a parameter's version counter moved or after training.
+        ver = sum(p._version for p in self.params)
+        if training and self._fresh_version is not None and ver == self._fresh_version and self._shadow_valid:
             pass        # the fused optimizer wrote the shadow together with the weights (optim.AdamW.step) and nothing changed since
-        elif training or ver != self._shadow_version:
+        elif training or not self._shadow_valid or ver != self._shadow_version:
             ops.cast_bf16(self.flat_param, out=self.flat_bf16)
+            self._shadow_valid, self._valid_version = True, ver
             self._shadow_version = None if training else ver
         self._fresh_version = None
-        if training and self._sentinel is not None and self._sentinel.grad is None:
+        if zero_grads and training and self._sentinel is not None and self._sentinel.grad is None:
             # the caller cleared the gradients (zero_grad(set_to_none=True)): start a fresh accumulation
             self.flat_grad.zero_()
             for p in self._touched:
@@ -126,11 +136,20 @@ class ParamArena:
         """Parameters were modified without bumping flat_param's version counter (e.g. through .data)."""
         self._shadow_version = None
         self._fresh_version = None
+        self._shadow_valid = False
 
     def shadow_is_fresh(self):
-        """Called by the fused optimizer: the bf16 shadow was written in the same pass as the fp32 weights, so the next training
-        step may skip its cast launch -- unless a parameter's version counter moves in between (load_state_dict, manual edits)."""
-        self._fresh_version = sum(p._version for p in self.params)
+        """Called by the fused optimizer: it wrote the bf16 shadow of every ACTIVE segment in the same pass as the fp32 weights.
+        The next training step may skip its cast launch only if the shadow was completely valid before that pass (a full cast
+        happened since build / mark_dirty) and no parameter's version counter moved since that cast (load_state_dict, manual
+        edits): otherwise inactive segments -- or everything, when the optimizer steps before the first forward like the
+        reference loop does (main_r2r.py:229-230) -- would still hold stale or uninitialised values."""
+        ver = sum(p._version for p in self.params)
+        if self._shadow_valid and ver == self._valid_version:
+            self._fresh_version = ver
+        else:
+            self._fresh_version = None
+            self._shadow_valid = False
         self._shadow_version = None
 
     def grads_are_zero(self):
@@ -185,4 +204,13 @@ class ParamArena:
 
     def next_seed(self):
         """Advance the device-resident dropout seed (one tiny in-place add; CUDA-graph friendly)."""
-        self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+        if not self.external_prologue:
+            self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+    def run_seed(self) -> torch.Tensor:
+        """A private copy of the current seed for ONE forward (Run): the backward kernels regenerate the dropout masks from the
+        pointer they are handed, so a forward that is followed by other forwards before its backward (the finetune agent runs
+        dozens of 'language' / 'history' / 'visual' calls and then one loss.backward(), agent_cmt.py:562) must not share a
+        seed cell that those later forwards advance.  Inside a captured graph the copy lives in the graph's memory pool and is
+        re-made from the live seed on every replay."""
+        return self.seed.clone()

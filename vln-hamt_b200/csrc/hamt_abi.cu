@@ -49,9 +49,9 @@ int hamt_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_
 
 int hamt_gemm_set_auto_pair(int on) { gemm_set_auto_pair(on); return 0; }
 
-int hamt_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd, int M,
-                int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
-  return ln_fwd(x, res, gamma, beta, y, z_out, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+int hamt_ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
+                float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
+  return ln_fwd(x, res, res32, gamma, beta, y, y32, z_out, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
 }
 int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
                 float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site, float p,
@@ -110,7 +110,6 @@ int hamt_embed_feat_bwd(const hamt_embed_feat_desc* d, const hamt_embed_feat_gra
   return embed_feat_bwd(a, (cudaStream_t)stream);
 }
 
-int hamt_ln_set_variant(int v) { ln_set_variant(v); return 0; }
 int hamt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream) { return cast_f32_to_bf16(in, out, n, (cudaStream_t)stream); }
 int hamt_colsum_bf16(const void* x, long long ld, float* out, int M, int N, void* stream) { return colsum_bf16(x, ld, out, M, N, (cudaStream_t)stream); }
 int hamt_mean_pool_fwd(const void* x, float* out, int N, int P, int H, void* stream) { return mean_pool_fwd(x, out, N, P, H, (cudaStream_t)stream); }

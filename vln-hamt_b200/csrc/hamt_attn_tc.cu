@@ -1,0 +1,574 @@
+// Blackwell-native fused attention for the HAMT hot path (head_dim 64): TMA-staged tiles, tcgen05.mma with the scores and the
+// output accumulator in TMEM, several (sequence, head) problems PACKED into one 128-row UMMA tile.
+//
+//   P = softmax(Q K^T * scale + mask);  O = dropout(P) V        (pretrain_src/model/vilmodel.py:96-129 self, :322-349 cross)
+//
+// Why packing: the problems of this model are tiny -- 36 x 36 (the 11 520 panorama problems of a batch), 53 x 53, 80 x 53, 16 x 80 --
+// so one problem fills a fraction of the 128-row tile the tensor core works on.  A tile therefore holds P problems:
+//
+//   rows (TMEM lanes, one softmax thread each)        columns of the score tile S = Qp Kp^T (fp32, TMEM)
+//   Sq <= 32 : 4 problems, one per warp (32-row slot)   problem p owns the key window [p*W, p*W + Sk),  W = Sk rounded up to 8
+//   Sq <= 40 : 3 problems, rows 0..31 of problem p in   (only the diagonal blocks of S are meaningful; the off-diagonal products
+//              warp p, the Sq-32 remaining rows of all   cost tensor-pipe time that is idle anyway: the kernel is bound by HBM
+//              three in warp 3 (lanes 8p .. 8p+7)         traffic and by the softmax ALU work, not by MMA issue)
+//   Sq <= 64 : 2 problems at rows 0 and 64
+//   else     : 1 problem per tile, Sq > 128 -> several 128-row tiles per problem (K / V re-read through L2)
+//
+// O = Pd V is ONE MMA over the packed key axis with a block-diagonal Pd: every softmax thread writes its whole row of Pd (bf16, K-major,
+// 128-byte swizzle) with zeros outside its own key window.
+//
+// Warp roles (320 threads, one persistent CTA per SM, static round-robin tile list):
+//   warp 0      TMA producer: Q / K / V boxes of the tile's problems straight out of the fused [tokens, 3H] projection buffer through
+//               3-D tensor maps (column, position, sequence) -- rows past the end of a sequence are zero-filled by the TMA unit, so the
+//               padding of the packed tile needs no extra pass -- into a ring of NS shared-memory stages;
+//   warp 1      TMEM owner and single-thread tcgen05.mma issuer: S = Q K^T as soon as a stage lands, O = Pd V as soon as the softmax
+//               warps publish Pd; order QK(i+1) before PV(i) so the tensor pipe never waits for the softmax of the same tile;
+//   warps 2-5 / 6-9   two softmax warpgroups working on alternate tiles (each has its own S / O TMEM columns and Pd buffer): tcgen05.ld of the
+//               lane's key window -> scale + additive mask (divide-then-add, -10000 masks as in the reference) -> max / exp2 / sum with
+//               one thread per row (no shuffles) -> dropout on the probabilities -> Pd to shared memory -> later the O tile: tcgen05.ld,
+//               1/l scaling, bf16, swizzled staging, ONE TMA store per warp (rows past the sequence end are clipped by the TMA unit).
+// The log-sum-exp of every row is saved for the backward kernel (attn_bwd_tc_kernel below).
+#include <cuda.h>
+#include <stdio.h>
+#include "hamt_common.cuh"
+#include "hamt_kernels.h"
+
+namespace hamt {
+
+namespace tc {
+
+static constexpr int kThreads = 320;
+static constexpr int kLog2eNum = 0;  // (placeholder to keep the namespace non-empty for older compilers)
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes (st.shared) -> visible to the async proxy (UMMA operand reads, TMA stores)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Columns [0, w) of a TMEM row window into v[0 .. NCH*32): full 32-column chunks, then a tail of 8 / 16 / 24 columns (w is a
+// multiple of 8, warp-uniform); registers past w are set to zero.  The caller issues tmem_ld_wait() before reading v.
+template <int NCH>
+__device__ __forceinline__ void load_window(uint32_t taddr, int w, uint32_t (&v)[NCH * 32]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int rem = w - c * 32;
+    if (rem >= 32) {
+      tmem_ld_x32(taddr + c * 32, &v[c * 32]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[c * 32 + j] = 0u;
+      if (rem >= 16) {
+        tmem_ld_x16(taddr + c * 32, &v[c * 32]);
+        if (rem >= 24) tmem_ld_x8(taddr + c * 32 + 16, &v[c * 32 + 16]);
+      } else if (rem >= 8) {
+        tmem_ld_x8(taddr + c * 32, &v[c * 32]);
+      }
+    }
+  }
+}
+
+// tile geometry shared by the forward and backward kernels (filled on the host by plan())
+struct Geom {
+  int nprob, heads, Sq, Sk;
+  int W;          // key-window stride of a problem inside the packed key axis (Sk rounded up to 8)
+  int P;          // problems per tile
+  int regime;     // 0: 32-row slots (Sq <= 32), 1: 3 problems + shared remainder warp (Sq <= 40), 2: 64-row slots, 3: one problem per tile
+  int QT;         // 128-row query tiles per problem (regime 3)
+  int ntiles;
+  int n_total;    // packed key extent of the MMAs (P * W rounded up to 16)
+  int nwin;       // key windows the remainder warp of regime 1 has to look at (= P), else 1
+};
+
+struct FwdParams {
+  Geom g;
+  int ns;                 // input stages
+  int nwg;                // softmax warpgroups in use (2, or 1 when the score tile needs more than half of TMEM)
+  uint32_t stage_bytes, off_k, off_v;     // per input stage: Q at 0, K at off_k, V at off_v
+  uint32_t off_p, p_bytes;                // Pd buffers (one per warpgroup), from the start of dynamic smem
+  uint32_t off_mask, mask_floats;         // per softmax warp: nwin * NCH*32 floats
+  uint32_t off_bar;
+  uint32_t tx_q32, tx_q8, tx_kv;          // bytes of one Q box (32 rows), one remainder box (8 rows), one K or V box
+  int kv_box_rows;
+  float scale_log2;       // softmax scale * log2(e)
+  const float* mask;      // additive fp32 [B, Sk] or null
+  float* lse;             // fp32 [B, heads, Sq] or null
+  DropCfg drop;
+};
+
+// lane -> (problem slot inside the tile, query row of that problem); slot = TMEM lane quarter owned by the warp
+struct RowMap {
+  int pi;      // problem slot (0 .. P-1)
+  int qrow;    // query position inside the problem
+  bool ok;     // the lane maps to a row of the layout at all
+};
+__device__ __forceinline__ RowMap row_map(const Geom& g, int slot, int lane, int qt) {
+  RowMap r;
+  if (g.regime == 0) { r.pi = slot; r.qrow = lane; r.ok = lane < g.Sq; }
+  else if (g.regime == 1) {
+    if (slot < 3) { r.pi = slot; r.qrow = lane; r.ok = true; }
+    else { r.pi = lane >> 3; r.qrow = 32 + (lane & 7); r.ok = r.pi < 3 && r.qrow < g.Sq; }
+  } else if (g.regime == 2) { r.pi = slot >> 1; r.qrow = (slot & 1) * 32 + lane; r.ok = r.qrow < g.Sq; }
+  else { r.pi = 0; r.qrow = qt * 128 + slot * 32 + lane; r.ok = r.qrow < g.Sq; }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qr, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_or,
+                   const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base + p.off_bar;
+  // barriers: full[ns], empty[ns], s_full[2], p_full[2], o_full[2], o_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.ns + s); };
+  auto sfull_bar = [&](int w) { return bar_base + 8u * (2 * p.ns + w); };
+  auto pfull_bar = [&](int w) { return bar_base + 8u * (2 * p.ns + 2 + w); };
+  auto ofull_bar = [&](int w) { return bar_base + 8u * (2 * p.ns + 4 + w); };
+  auto oempty_bar = [&](int w) { return bar_base + 8u * (2 * p.ns + 6 + w); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.ns + 8);
+
+  if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) { printf("hamt attn: dynamic smem base not 1024-byte aligned\n"); __trap(); }
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
+    if (g.regime == 1) { tma_prefetch_desc(&tm_qr); tma_prefetch_desc(&tm_or); }
+    for (int s = 0; s < p.ns; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(sfull_bar(w), 1); mbar_init(pfull_bar(w), 4); mbar_init(ofull_bar(w), 1); mbar_init(oempty_bar(w), 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_addr);
+  // K / V stages start from zeros: rows of the packed key axis that no TMA box ever writes (alignment padding, absent problems of a
+  // partial last tile) must hold finite values -- they meet zero probabilities in the PV product
+  for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)p.ns * p.stage_bytes; i += kThreads * 16u)
+    *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_grid_sync();   // everything above overlapped the previous kernel
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  const int heads = g.heads;
+  const int n_my = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int kch = (g.n_total + 63) >> 6;         // 64-key chunks of Pd
+  // TMEM columns: warpgroup w: S at w*256, O at w*256 + 192 (two warpgroups, n_total <= 192); single warpgroup: S at 0, O at 448
+  auto s_col = [&](int w) { return (uint32_t)(p.nwg == 2 ? w * 256 : 0); };
+  auto o_col = [&](int w) { return (uint32_t)(p.nwg == 2 ? w * 256 + 192 : 448); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % p.ns;
+        const uint32_t ph = (uint32_t)(i / p.ns) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int grp = tile / g.QT, qt = tile % g.QT;
+        const int p0 = grp * g.P;
+        const int np = min(g.P, g.nprob - p0);
+        const uint32_t sq = smem_base + (uint32_t)s * p.stage_bytes, sk = sq + p.off_k, sv = sq + p.off_v;
+        // byte count first (expect_tx), then the copies
+        uint32_t bytes = 0;
+        for (int pi = 0; pi < np; ++pi) {
+          if (g.regime == 0) bytes += p.tx_q32;
+          else if (g.regime == 1) bytes += p.tx_q32 + p.tx_q8;
+          else if (g.regime == 2) bytes += 2 * p.tx_q32;
+          else for (int k = 0; k < 4; ++k) if (qt * 128 + k * 32 < g.Sq) bytes += p.tx_q32;
+          bytes += 2 * p.tx_kv;
+        }
+        mbar_expect_tx(full_bar(s), bytes);
+        for (int pi = 0; pi < np; ++pi) {
+          const int pr = p0 + pi, b = pr / heads, h = pr % heads;
+          if (g.regime == 0) tma_load_3d(sq + pi * 4096u, &tm_q, h * 64, 0, b, full_bar(s));
+          else if (g.regime == 1) {
+            tma_load_3d(sq + pi * 4096u, &tm_q, h * 64, 0, b, full_bar(s));
+            tma_load_3d(sq + 96u * 128u + pi * 1024u, &tm_qr, h * 64, 32, b, full_bar(s));
+          } else if (g.regime == 2) {
+            tma_load_3d(sq + pi * 8192u, &tm_q, h * 64, 0, b, full_bar(s));
+            tma_load_3d(sq + pi * 8192u + 4096u, &tm_q, h * 64, 32, b, full_bar(s));
+          } else {
+            for (int k = 0; k < 4; ++k)
+              if (qt * 128 + k * 32 < g.Sq) tma_load_3d(sq + k * 4096u, &tm_q, h * 64, qt * 128 + k * 32, b, full_bar(s));
+          }
+          tma_load_3d(sk + (uint32_t)(pi * g.W) * 128u, &tm_k, h * 64, 0, b, full_bar(s));
+          tma_load_3d(sv + (uint32_t)(pi * g.W) * 128u, &tm_v, h * 64, 0, b, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc_s = umma_idesc_bf16(128, g.n_total, false, false);     // S = Q (K-major) x K^T (K-major)
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);             // O = Pd (K-major) x V (MN-major: d contiguous)
+      auto issue_pv = [&](int j) {
+        const int w = j % p.nwg, s = j % p.ns;
+        const uint32_t use = (uint32_t)(j / p.nwg);          // how many tiles this warpgroup has handled before
+        mbar_wait(pfull_bar(w), use & 1u);                   // Pd of tile j is in shared memory (and S of tile j has been read)
+        mbar_wait(oempty_bar(w), (use & 1u) ^ 1u);           // the O accumulator of this warpgroup's previous tile has been drained
+        tc_fence_after();
+        const uint32_t sv = smem_base + (uint32_t)s * p.stage_bytes + p.off_v;
+        const uint32_t sp = smem_base + p.off_p + (uint32_t)w * p.p_bytes;
+        const uint32_t d_tmem = tmem_base + o_col(w);
+        const int ksteps = g.n_total >> 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = umma_smem_desc(sp + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u, 16, 1024);
+          const uint64_t db = umma_smem_desc(sv + (uint32_t)k * 2048u, 8192, 1024);
+          umma_bf16(d_tmem, da, db, idesc_o, k > 0 ? 1u : 0u);
+        }
+        umma_commit(ofull_bar(w));
+        umma_commit(empty_bar(s));            // Q / K / V of this stage are no longer needed
+      };
+      for (int i = 0; i < n_my; ++i) {
+        const int w = i % p.nwg, s = i % p.ns;
+        mbar_wait(full_bar(s), (uint32_t)(i / p.ns) & 1u);
+        // S columns of warpgroup w are free: Pd of its previous tile was published (waited for in issue_pv(i - nwg)) after S was read
+        tc_fence_after();
+        const uint32_t sq = smem_base + (uint32_t)s * p.stage_bytes, sk = sq + p.off_k;
+        const uint32_t d_tmem = tmem_base + s_col(w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = umma_smem_desc(sq + k * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc(sk + k * 32, 16, 1024);
+          umma_bf16(d_tmem, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(sfull_bar(w));
+        if (i >= p.nwg - 1 && i - (p.nwg - 1) >= 0 && p.nwg == 2) { if (i >= 1) issue_pv(i - 1); }
+        else if (p.nwg == 1) issue_pv(i);
+      }
+      if (p.nwg == 2 && n_my > 0) issue_pv(n_my - 1);
+    }
+  } else {
+    // ===================== softmax + output warps =====================
+    const int wg = (warp - 2) >> 2;              // warpgroup 0: warps 2..5, warpgroup 1: warps 6..9
+    const int slot = warp & 3;                   // TMEM lane quarter this warp may access = 32-row slot of the tile
+    if (wg < p.nwg) {
+      const DropState ds = drop_init(p.drop);
+      const bool multi = g.regime == 1 && slot == 3;
+      float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)((warp - 2) * p.mask_floats);
+      uint8_t* pbuf = smem_raw + p.off_p + (uint32_t)wg * p.p_bytes;
+      const uint32_t pbuf_a = smem_base + p.off_p + (uint32_t)wg * p.p_bytes;
+      const int row = slot * 32 + lane;          // row of the tile = TMEM lane
+      const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
+      int use = 0;
+      for (int i = wg; i < n_my; i += p.nwg, ++use) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int grp = tile / g.QT, qt = tile % g.QT;
+        const int p0 = grp * g.P;
+        const RowMap rm = row_map(g, slot, lane, qt);
+        const int pr = p0 + rm.pi;
+        const bool valid = rm.ok && pr < g.nprob;
+        const int b = valid ? pr / heads : 0, h = valid ? pr % heads : 0;
+        // ---- additive mask rows of the key window(s) this warp looks at, in log2 units; padded keys carry -inf
+        {
+          const int nw = multi ? g.nwin : 1;
+          for (int wdx = 0; wdx < nw; ++wdx) {
+            const int prw = multi ? p0 + wdx : __shfl_sync(0xffffffffu, pr, 0);
+            const bool okw = multi ? (prw < g.nprob) : __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
+            const int bw = okw ? prw / heads : 0;
+            for (int j = lane; j < NCH * 32; j += 32) {
+              float mv = -INFINITY;
+              if (j < g.Sk) mv = (p.mask != nullptr && okw) ? p.mask[(long long)bw * g.Sk + j] * 1.4426950408889634f : 0.f;
+              smask[wdx * NCH * 32 + j] = mv;
+            }
+          }
+          // the previous tile's output store must have finished READING the staging rows (they alias this warp's Pd rows)
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+        mbar_wait(sfull_bar(wg), (uint32_t)use & 1u);
+        tc_fence_after();
+        // ---- scores of this lane's key window
+        uint32_t sv[NCH * 32];
+        const uint32_t t_s = tmem_base + lane_field + s_col(wg);
+        if (!multi) {
+          load_window<NCH>(t_s + (uint32_t)(__shfl_sync(0xffffffffu, rm.pi, 0) * g.W), g.W, sv);
+          tmem_ld_wait();
+        } else {
+          // remainder warp: its lanes belong to different problems -> fetch every window chunk-wise and keep the lane's own
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t t0[32], t1[32], t2[32];
+            const int rem = g.W - c * 32;
+            if (rem > 0) {
+              // (windows are read with full 32-column loads here: columns past a window are the next window / padding, never used)
+              tmem_ld_x32(t_s + 0 * g.W + c * 32, t0);
+              tmem_ld_x32(t_s + 1 * g.W + c * 32, t1);
+              tmem_ld_x32(t_s + 2 * g.W + c * 32, t2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sv[c * 32 + j] = (c * 32 + j < g.W) ? (rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j])) : 0u;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sv[c * 32 + j] = 0u;
+            }
+          }
+        }
+        const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NCH * 32; ++j) {
+          const float t = fmaf(__uint_as_float(sv[j]), p.scale_log2, mrow[j]);      // padded keys: 0 * c + (-inf)
+          sv[j] = __float_as_uint(t);
+          mx = fmaxf(mx, t);
+        }
+        float l = 0.f;
+        const unsigned long long rbase = ((unsigned long long)pr * g.Sq + rm.qrow) * g.Sk;
+#pragma unroll
+        for (int j = 0; j < NCH * 32; ++j) {
+          const float pe = ex2_approx(__uint_as_float(sv[j]) - mx);
+          l += pe;
+          float pd = pe;
+          if (ds.on) pd *= drop_mult(ds, rbase + j);
+          sv[j] = __float_as_uint(pd);
+        }
+        // ---- this lane's row of Pd: zeros outside its key window (16-byte units of 8 keys; unit u of row r lives at chunk u>>3,
+        //      byte r*128 + ((u&7) ^ (r&7))*16: the 128-byte swizzle the UMMA descriptor expects)
+        {
+          const int u0 = valid ? (rm.pi * g.W) >> 3 : 0x7fffffff, nu = g.W >> 3, units = kch * 8;
+          for (int u = 0; u < units; ++u) {
+            uint4 val = make_uint4(0, 0, 0, 0);
+            const int k = u - u0;
+            if (k >= 0 && k < nu) {
+              // static register indexing: the unit of the window is selected with an unrolled compare chain
+#pragma unroll
+              for (int kk = 0; kk < NCH * 4; ++kk)
+                if (kk == k)
+                  val = make_uint4(pack_bf16(__uint_as_float(sv[kk * 8 + 0]), __uint_as_float(sv[kk * 8 + 1])),
+                                   pack_bf16(__uint_as_float(sv[kk * 8 + 2]), __uint_as_float(sv[kk * 8 + 3])),
+                                   pack_bf16(__uint_as_float(sv[kk * 8 + 4]), __uint_as_float(sv[kk * 8 + 5])),
+                                   pack_bf16(__uint_as_float(sv[kk * 8 + 6]), __uint_as_float(sv[kk * 8 + 7])));
+            }
+            *reinterpret_cast<uint4*>(pbuf + (uint32_t)(u >> 3) * 16384u + (uint32_t)row * 128u + (uint32_t)(((u & 7) ^ (row & 7)) << 4)) = val;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar(wg));
+        if (valid && p.lse != nullptr) p.lse[(long long)pr * g.Sq + rm.qrow] = (mx + __log2f(l)) * 0.6931471805599453f;
+        // ---- output tile
+        mbar_wait(ofull_bar(wg), (uint32_t)use & 1u);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        const uint32_t t_o = tmem_base + lane_field + o_col(wg);
+        tmem_ld_x32(t_o, o0);
+        tmem_ld_x32(t_o + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(oempty_bar(wg));
+        const float inv = 1.0f / l;
+        uint8_t* srow = pbuf + (uint32_t)row * 128u;          // staging = chunk 0 of this warpgroup's Pd buffer (PV has completed)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t* src = c < 4 ? &o0[c * 8] : &o1[(c - 4) * 8];
+          *reinterpret_cast<uint4*>(srow + (((uint32_t)c ^ (uint32_t)(row & 7)) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv), pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv),
+                         pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv), pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t sst = pbuf_a + (uint32_t)(slot * 32) * 128u;
+          if (!multi) {
+            const int pr0 = p0 + rm.pi;        // lane 0's problem = the warp's problem
+            const int q0 = rm.qrow;            // first query row of this warp's slot
+            if (pr0 < g.nprob && q0 < g.Sq) tma_store_3d(&tm_o, sst, (pr0 % heads) * 64, q0, pr0 / heads);
+          } else {
+            for (int wdx = 0; wdx < 3; ++wdx)
+              if (p0 + wdx < g.nprob) tma_store_3d(&tm_or, sst + (uint32_t)wdx * 1024u, ((p0 + wdx) % heads) * 64, 32, (p0 + wdx) / heads);
+          }
+          tma_store_commit();
+        }
+        (void)b; (void)h;
+      }
+      if (lane == 0) tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// bf16 tensor seen as [B][S][heads*64] with row pitch ld and sequence stride bs (elements); box = box_rows x 64 columns of one sequence
+static int make_map3(CUtensorMap* tm, const void* ptr, int B, int S, int heads, long long ld, long long bs, int box_rows) {
+  PFN_encodeTiled enc = encode_fn();
+  HAMT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {(cuuint64_t)heads * 64, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (B == 1) gstr[1] = (cuuint64_t)ld * 2 * (cuuint64_t)S;      // unused stride must still be a multiple of 16 bytes
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "attn: cuTensorMapEncodeTiled failed (%d) B=%d S=%d heads=%d ld=%lld bs=%lld box=%d", (int)r, B, S, heads, ld, bs, box_rows);
+    set_last_error(buf);
+    return -2;
+  }
+  return 0;
+}
+
+// packing plan for (Sq, Sk); max_ntotal bounds the packed key axis (forward: 192 with two warpgroups)
+static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal) {
+  g.nprob = B * heads; g.heads = heads; g.Sq = Sq; g.Sk = Sk;
+  g.W = (Sk + 7) & ~7;
+  if (g.W > 128) return false;                 // longer key axes: legacy kernel (RxR instructions)
+  if (Sq <= 32) { g.regime = 0; g.P = 4; }
+  else if (Sq <= 40) { g.regime = 1; g.P = 3; }
+  else if (Sq <= 64) { g.regime = 2; g.P = 2; }
+  else { g.regime = 3; g.P = 1; }
+  // the packed key axis must fit the score tile; fall back to fewer problems per tile (regime 2 / 3 layouts)
+  while (g.P > 1 && ((g.P * g.W + 15) & ~15) > max_ntotal) {
+    if (g.regime == 1) { g.regime = 2; g.P = 2; }
+    else if (g.regime == 0 && g.P == 4) { g.P = 2; }          // slots 0 and 1 only
+    else if (g.regime == 0 && g.P == 2) { g.P = 1; }
+    else { g.regime = 3; g.P = 1; }
+  }
+  if (((g.P * g.W + 15) & ~15) > max_ntotal) return false;
+  g.n_total = (g.P * g.W + 15) & ~15;
+  g.QT = g.regime == 3 ? (Sq + 127) / 128 : 1;
+  g.ntiles = ((g.nprob + g.P - 1) / g.P) * g.QT;
+  g.nwin = g.regime == 1 ? 3 : 1;
+  return true;
+}
+
+static int g_attn_impl = 0;        // hamt_attn_set_impl: 0 = auto (tcgen05 kernels where the shape fits), 1 = legacy mma.sync kernels only
+
+static int num_sms_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int NCH>
+static int launch_fwd(const AttnArgs& a, const Geom& g, cudaStream_t st) {
+  FwdParams p{};
+  p.g = g;
+  p.nwg = 2;
+  const uint32_t krows = (uint32_t)g.n_total;                       // rows of the packed K / V tiles
+  p.off_k = 16384u;
+  p.off_v = p.off_k + krows * 128u;
+  p.stage_bytes = p.off_v + krows * 128u;
+  p.p_bytes = (uint32_t)((g.n_total + 63) / 64) * 16384u;
+  p.mask_floats = (uint32_t)(g.nwin * NCH * 32);
+  const uint32_t fixed = 2 * p.p_bytes + 8u * p.mask_floats * 4u + 256u;
+  int ns = (int)((232448u - 1024u - fixed) / p.stage_bytes);
+  if (ns > 4) ns = 4;
+  HAMT_REQUIRE(ns >= 2, "attn_fwd (tcgen05): shape does not fit two input stages");
+  p.ns = ns;
+  p.off_p = (uint32_t)ns * p.stage_bytes;
+  p.off_mask = p.off_p + 2 * p.p_bytes;
+  p.off_bar = (p.off_mask + 8u * p.mask_floats * 4u + 15u) & ~15u;
+  const size_t smem = p.off_bar + 256;
+  p.tx_q32 = 32 * 128; p.tx_q8 = 8 * 128; p.tx_kv = (uint32_t)g.W * 128u; p.kv_box_rows = g.W;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.mask = a.mask; p.lse = a.lse;
+  p.drop = DropCfg{a.drop.seed_ptr, a.drop.site, a.drop.p};
+  CUtensorMap tq, tqr, tk, tv, to, tor;
+  int rc;
+  if ((rc = make_map3(&tq, a.q, a.B, a.Sq, a.heads, a.ldq, a.q_bstride, 32))) return rc;
+  if ((rc = make_map3(&tqr, a.q, a.B, a.Sq, a.heads, a.ldq, a.q_bstride, 8))) return rc;
+  if ((rc = make_map3(&tk, a.k, a.B, a.Sk, a.heads, a.ldkv, a.kv_bstride, g.W))) return rc;
+  if ((rc = make_map3(&tv, a.v, a.B, a.Sk, a.heads, a.ldkv, a.kv_bstride, g.W))) return rc;
+  if ((rc = make_map3(&to, a.out, a.B, a.Sq, a.heads, a.ldo, a.o_bstride, 32))) return rc;
+  if ((rc = make_map3(&tor, a.out, a.B, a.Sq, a.heads, a.ldo, a.o_bstride, 8))) return rc;
+  auto kern = attn_fwd_tc_kernel<NCH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    attr_set = true;
+  }
+  const int grid = g.ntiles < num_sms_cached() ? g.ntiles : num_sms_cached();
+  launch_pdl(kern, grid, kThreads, smem, st, tq, tqr, tk, tv, to, tor, p);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+}  // namespace tc
+
+void attn_set_impl(int v) { tc::g_attn_impl = v; }
+
+// returns 1 when the tcgen05 forward took the problem (status in *rc), 0 when the caller should run the legacy kernel
+int attn_fwd_tc(const AttnArgs& a, cudaStream_t st, int* rc) {
+  if (tc::g_attn_impl == 1) return 0;
+  tc::Geom g;
+  if (!tc::plan(g, a.B, a.heads, a.Sq, a.Sk, 192)) return 0;
+  const int nch = (g.W + 31) / 32;
+  if (nch == 1) *rc = tc::launch_fwd<1>(a, g, st);
+  else if (nch == 2) *rc = tc::launch_fwd<2>(a, g, st);
+  else if (nch == 3) *rc = tc::launch_fwd<3>(a, g, st);
+  else *rc = tc::launch_fwd<4>(a, g, st);
+  return 1;
+}
+
+}  // namespace hamt

@@ -84,7 +84,8 @@ enum : int {
 
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL wide epilogue (EW = 16; opt-in through hamt_gemm_set_wide_epilogue, not selected by default, not yet measured).
+// Wide epilogue (EW = 16), used for the dGELU dgrad (measured 270 -> 183 us at M = 34 560, profiles/r02_kbench_variants.txt; it lost on
+// the store / GELU / accumulate epilogues, which keep the 8-warp version).
 // The GELU / dGELU epilogues are ALU-bound (2 MUFU + ~20 ALU per element; profiles/r01_ncu_ffn_gemms_v6.txt: 272 us against a
 // 116 us tensor-pipe floor at M = 34 560) and with 8 warps only two warps per scheduler hide each other's latencies (issue slots
 // 36 % busy).  Here 16 warps share a 128 x 256 accumulator: warp e owns TMEM lane quarter (warp & 3) and the 64-column slice e >> 2,
@@ -237,7 +238,7 @@ __device__ __forceinline__ void epilogue_wide(const GemmParams& p, uint8_t* stag
 
 // Register budget: 10 warps land 3 + 3 + 2 + 2 on the four SM sub-partitions (16 K registers each), so __launch_bounds__(320, 1) caps
 // ptxas at 168 registers; asking for more ("too many resources requested for launch") does not fit 3 warps x 32 lanes.
-// EW = epilogue warps: 8 (each warp owns a 32-row x BN/2 slab, 64-column groups) or 16 (EXPERIMENTAL wide epilogue, see epilogue_wide).
+// EW = epilogue warps: 8 (each warp owns a 32-row x BN/2 slab, 64-column groups) or 16 (wide epilogue of the dGELU dgrad, see epilogue_wide).
 template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI, int EW = kEpiWarps>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
@@ -756,7 +757,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
 
 static bool g_auto_pair = true;    // hamt_gemm_set_auto_pair(0) restricts the cost model to single-CTA tiles
 void gemm_set_auto_pair(int on) { g_auto_pair = on != 0; }
-static bool g_wide_epi = false;    // hamt_gemm_set_wide_epilogue(1): EXPERIMENTAL 16-warp epilogue for aligned 256-wide bf16-store GEMMs
+static bool g_wide_epi = true;     // hamt_gemm_set_wide_epilogue(0): 8-warp epilogue also for the dGELU dgrad (A/B measurements)
 void gemm_set_wide_epilogue(int on) { g_wide_epi = on != 0; }
 static int g_num_sms = 0;
 static int g_sm_limit = 0;        // hamt_gemm_set_sm_limit: persistent GEMM grids use at most this many SMs (0 = all)
@@ -882,8 +883,8 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
     else if (p.act == 1 && p.aux_mode == 1 && p.out_mode == 0 && p.colsum == nullptr) epi = EPI_GELU_PRE;
     else if (p.act == 0 && p.aux_mode == 2 && p.out_mode == 0) epi = EPI_DGELU;
   }
-  // EXPERIMENTAL wide epilogue: fully aligned problems only (no guards in epilogue_wide)
-  if (g_wide_epi && bn == 256 && (epi == EPI_STORE || epi == EPI_GELU_PRE || epi == EPI_DGELU || epi == EPI_ACCUM)) {
+  // 16-warp epilogue for the dGELU dgrad: fully aligned problems only (no guards in epilogue_wide)
+  if (g_wide_epi && bn == 256 && epi == EPI_DGELU) {
     const int tm_rows = pair ? 2 * BM : BM;
     const bool aligned = a.M % tm_rows == 0 && a.N % 256 == 0 && (((uintptr_t)p.out | (uintptr_t)p.aux | (uintptr_t)p.colsum | (uintptr_t)p.bias) & 15) == 0 &&
                          p.ldo % 8 == 0 && (p.aux == nullptr || p.ld_aux % 8 == 0);
@@ -893,11 +894,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
     if (pair) return launch<256, AMN_, BMN_, true, EPI_, 16>(ta, tb, p, st);               \
     return launch<256, AMN_, BMN_, false, EPI_, 16>(ta, tb, p, st);                        \
   }
-      HAMT_WIDE(false, false, EPI_STORE)
-      HAMT_WIDE(false, false, EPI_GELU_PRE)
-      HAMT_WIDE(false, true, EPI_STORE)
       HAMT_WIDE(false, true, EPI_DGELU)
-      HAMT_WIDE(false, true, EPI_ACCUM)
 #undef HAMT_WIDE
     }
   }

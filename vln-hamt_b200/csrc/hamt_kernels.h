@@ -27,8 +27,9 @@ void gemm_set_wide_epilogue(int on);
 struct DropArgs { const unsigned long long* seed_ptr; unsigned int site; float p; };
 
 // y = LN(drop(x) + res) * gamma + beta ; optionally stores z = drop(x)+res (bf16; may alias x) and row stats
-int ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd,
-           int M, int H, float eps, DropArgs drop, cudaStream_t st);
+// res32 (fp32, instead of res) / y32 (fp32 copy of y): the full-precision residual stream, either may be null
+int ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
+           float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st);
 // backward of the above.  dx = grad wrt x (dropout applied), dres = grad wrt res (+ dres_in), column sums accumulated
 // atomically into dgamma/dbeta/dbias (fp32, may be null).
 int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx,
@@ -91,7 +92,6 @@ struct EmbedFeatBwdArgs {
 int embed_feat_bwd(const EmbedFeatBwdArgs& a, cudaStream_t st);
 
 // misc bandwidth kernels
-void ln_set_variant(int v);
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 int colsum_bf16(const void* x, long long ld, float* out, int M, int N, cudaStream_t st);          // out[n] += sum_m x[m,n]
 int mean_pool_fwd(const void* x, float* out, int N, int P, int H, cudaStream_t st);                // bf16 [N,P,H] -> fp32 [N,H]

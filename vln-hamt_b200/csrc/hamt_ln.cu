@@ -46,10 +46,16 @@ __device__ __forceinline__ void load_vec_f32(const float* p, int lane, float (&v
   }
 }
 
+// The residual stream may be carried in fp32 next to its bf16 copy: `res32` (fp32 [M,H]) replaces `res`, and `y32` receives the
+// un-rounded LayerNorm output for the next block's residual add.  The GEMMs still read the bf16 `y`; only the skip connection keeps
+// full precision, which is what torch.autocast does to the reference (layer_norm runs in fp32 there) -- with a bf16-only stream the
+// logits sit 1.2 .. 1.7x further from the fp32 reference than the reference's own autocast run, with the fp32 stream 0.5 .. 1.0x
+// (measured with the bf16-regime oracle).
 template <int NCH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* may alias z_out */, const __nv_bfloat16* __restrict__ res,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     __nv_bfloat16* __restrict__ y, __nv_bfloat16* z_out, float* __restrict__ mean_out,
+                                                     const float* __restrict__ res32, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                                                     __nv_bfloat16* z_out, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int M, float eps, DropCfg dc) {
   pdl_grid_sync();
   constexpr int H = NCH * 256;
@@ -68,7 +74,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
     }
-    if (res != nullptr) {
+    if (res32 != nullptr) {
+      float r[NCH * 8];
+      load_vec_f32<NCH>(res32 + (long long)row * H, lane, r);
+#pragma unroll
+      for (int i = 0; i < NCH * 8; ++i) z[i] += r[i];
+    } else if (res != nullptr) {
       float r[NCH * 8];
       load_row_bf16<NCH>(res + (long long)row * H, lane, r);
 #pragma unroll
@@ -87,6 +98,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
 #pragma unroll
     for (int i = 0; i < NCH * 8; ++i) o[i] = (z[i] - mean) * rstd * g[i] + b[i];
     store_row_bf16<NCH>(y + (long long)row * H, lane, o);
+    if (y32 != nullptr) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float* p32 = y32 + (long long)row * H + c * 256 + lane * 8;
+        *reinterpret_cast<float4*>(p32) = make_float4(o[c * 8], o[c * 8 + 1], o[c * 8 + 2], o[c * 8 + 3]);
+        *reinterpret_cast<float4*>(p32 + 4) = make_float4(o[c * 8 + 4], o[c * 8 + 5], o[c * 8 + 6], o[c * 8 + 7]);
+      }
+    }
     if (lane == 0) {
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
@@ -94,163 +113,118 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
   }
 }
 
+// Backward of y = LN(dropout(x) + res): persistent (one 8-warp CTA per SM, each warp walks rows with stride = total warps).
+// Round-1 version of this kernel ran at 1.2 TB/s for the small-M launches that make up 40 of its 44 launches per step
+// (profiles/r01_kbench_v5.txt; round-2 measurement of its variants in profiles/r02_kbench_variants.txt): it launched M/32 CTAs that
+// need ~240 registers (one CTA per SM) -> 160 CTAs = two waves at M = 5120, each wave a serial chain of 4 rows x (load, reduce, load,
+// store) with nothing in flight, and folded its column sums with 72 shared-memory fp32 atomics per lane (CAS loops on sm_100).  Here:
+//   * the grid never exceeds the SM count (one wave), rows are distributed over all warps of the chip;
+//   * the NEXT row's dy / z / residual-gradient chunks are requested (raw bf16, 36 registers) before the current row is reduced, so
+//     every warp always has one row in flight (8 warps x 4.6 KB per SM);
+//   * the second phase recomputes xhat / gamma*dy from the raw chunks instead of keeping 48 fp32 values alive;
+//   * column sums (dgamma, dbeta, dbias) stay in registers across rows and are folded once per CTA through warp-private,
+//     bank-conflict-free shared slabs (no shared atomics), then one red.global.add.v4.f32 per 4 columns and CTA.
 template <int NCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
-                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                     const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
-                                                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
-                                                     float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
-  pdl_grid_sync();
-  constexpr int H = NCH * 256;
-  __shared__ float sacc[3][H];
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const DropState ds = drop_init(dc);
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&sacc[0][0])[i] = 0.f;
-  __syncthreads();
-  float g[NCH * 8];
-  load_vec_f32<NCH>(gamma, lane, g);
-  float acc_g[NCH * 8], acc_b[NCH * 8], acc_x[NCH * 8];
-#pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
-    float d[NCH * 8], zz[NCH * 8];
-    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
-    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NCH * 8; ++i) {
-      const float xh = (zz[i] - mean) * rstd;
-      const float gd = d[i] * g[i];
-      acc_g[i] += d[i] * xh;
-      acc_b[i] += d[i];
-      s1 += gd;
-      s2 += gd * xh;
-      zz[i] = xh;
-      d[i] = gd;
-    }
-    s1 = warp_sum(s1) * (1.0f / H);
-    s2 = warp_sum(s2) * (1.0f / H);
-    float dz[NCH * 8];
-#pragma unroll
-    for (int i = 0; i < NCH * 8; ++i) dz[i] = rstd * (d[i] - s1 - zz[i] * s2);
-    if (dres != nullptr) {
-      float o[NCH * 8];
-      if (dres_in != nullptr) {
-        load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
-#pragma unroll
-        for (int i = 0; i < NCH * 8; ++i) o[i] += dz[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < NCH * 8; ++i) o[i] = dz[i];
-      }
-      store_row_bf16<NCH>(dres + (long long)row * H, lane, o);
-    }
-    if (dx != nullptr) {
-      if (ds.on) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dz[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
-      }
-      // bias gradient is the column sum of the *rounded* dx the wgrad GEMM will also see
-#pragma unroll
-      for (int i = 0; i < NCH * 8; ++i) acc_x[i] += dz[i];
-      store_row_bf16<NCH>(dx + (long long)row * H, lane, dz);
-    }
-  }
-  // cross-warp reduction through shared memory, then one atomic per column per CTA
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = c * 256 + lane * 8 + j;
-      atomicAdd(&sacc[0][col], acc_g[c * 8 + j]);
-      atomicAdd(&sacc[1][col], acc_b[c * 8 + j]);
-      atomicAdd(&sacc[2][col], acc_x[c * 8 + j]);
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, sacc[0][i]);
-    if (dbeta) atomicAdd(dbeta + i, sacc[1][i]);
-    if (dbias) atomicAdd(dbias + i, sacc[2][i]);
-  }
-}
-
-// EXPERIMENTAL variant of ln_bwd_kernel (opt-in through hamt_ln_set_variant(1); default off, unmeasured).  Same arithmetic, two
-// scheduling changes aimed at the small-M launches (M = 2.5 k .. 8.5 k rows, 26 us at 1.2 TB/s -- 40 of the 44 launches per step):
-//   * the residual-path gradient row (dres_in) is requested together with dy and z instead of after the two warp reductions
-//     (one exposed HBM latency per row less);
-//   * the cross-warp reduction at the end goes through warp-private shared slabs [warp][3][NCH*8][32] (value index major, lane minor:
-//     32 consecutive banks per store) that the CTA folds afterwards; ln_bwd_kernel uses 72 shared fp32 atomics per lane on a row-major
-//     [3][H] array -- 8-way bank conflicts, and every shared fp32 atomic is a compare-and-swap spin loop on sm_100 (ATOMS.CAST.SPIN).
-// OCC2: compile for two resident CTAs per SM (128 registers, some spills) instead of one (246 registers; the default kernel also needs
-// 238 and therefore runs 8 warps per SM) -- which of the two wins is a measurement for round 2.
-template <int NCH, bool OCC2>
-__global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+__global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                                                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                         const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
                                                         __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                         float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
   pdl_grid_sync();
   constexpr int H = NCH * 256;
-  constexpr int NV = NCH * 8;                 // values per lane
-  extern __shared__ float slab_all[];                 // [warps][3][NV][32]: warp-private, written once at the end (no atomics: fp32
-                                                      // shared-memory atomics are compare-and-swap loops on sm_100)
-  const int lane = threadIdx.x & 31;
+  constexpr int NV = NCH * 8;                          // values per lane
+  extern __shared__ float slab_all[];                  // [warps][3][NV][32] warp-private, written once at the end
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const DropState ds = drop_init(dc);
+  const bool has_in = dres != nullptr && dres_in != nullptr;
   float g[NV];
   load_vec_f32<NCH>(gamma, lane, g);
   float acc_g[NV], acc_b[NV], acc_x[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc_g[i] = acc_b[i] = acc_x[i] = 0.f;
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
-    float d[NV], zz[NV], o[NV];
-    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
-    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
-    if (dres != nullptr && dres_in != nullptr) load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
-    else {
+  const int stride = gridDim.x * wpb;
+  int row = blockIdx.x * wpb + warp;
+  uint4 nd[NCH], nz[NCH], nr[NCH];
+  float nmean = 0.f, nrstd = 0.f;
+  auto issue = [&](int r) {
+    const long long o = (long long)r * H + lane * 8;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) o[i] = 0.f;
+    for (int c = 0; c < NCH; ++c) {
+      nd[c] = *reinterpret_cast<const uint4*>(dy + o + c * 256);
+      nz[c] = *reinterpret_cast<const uint4*>(z + o + c * 256);
+      if (has_in) nr[c] = *reinterpret_cast<const uint4*>(dres_in + o + c * 256);
     }
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    nmean = mean_in[r];
+    nrstd = rstd_in[r];
+  };
+  auto unpack8 = [](const uint4& w, float (&f)[8]) {
+    const float2 a = unpack_bf16(w.x), b = unpack_bf16(w.y), c = unpack_bf16(w.z), d = unpack_bf16(w.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  };
+  auto pack8 = [](const float (&f)[8]) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  };
+  if (row < M) issue(row);
+  for (; row < M; row += stride) {
+    uint4 cd[NCH], cz[NCH], cr[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cz[c] = nz[c]; cr[c] = has_in ? nr[c] : make_uint4(0, 0, 0, 0); }
+    const float mean = nmean, rstd = nrstd;
+    if (row + stride < M) issue(row + stride);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float xh = (zz[i] - mean) * rstd;
-      const float gd = d[i] * g[i];
-      acc_g[i] += d[i] * xh;
-      acc_b[i] += d[i];
-      s1 += gd;
-      s2 += gd * xh;
-      zz[i] = xh;
-      d[i] = gd;
+    for (int c = 0; c < NCH; ++c) {
+      float d[8], zz[8];
+      unpack8(cd[c], d);
+      unpack8(cz[c], zz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (zz[j] - mean) * rstd;
+        const float gd = d[j] * g[c * 8 + j];
+        acc_g[c * 8 + j] = fmaf(d[j], xh, acc_g[c * 8 + j]);
+        acc_b[c * 8 + j] += d[j];
+        s1 += gd;
+        s2 = fmaf(gd, xh, s2);
+      }
     }
     s1 = warp_sum(s1) * (1.0f / H);
     s2 = warp_sum(s2) * (1.0f / H);
-    float dz[NV];
+    const long long o = (long long)row * H + lane * 8;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) dz[i] = rstd * (d[i] - s1 - zz[i] * s2);
-    if (dres != nullptr) {
+    for (int c = 0; c < NCH; ++c) {
+      float d[8], zz[8], dz[8];
+      unpack8(cd[c], d);
+      unpack8(cz[c], zz);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) o[i] += dz[i];
-      store_row_bf16<NCH>(dres + (long long)row * H, lane, o);
-    }
-    if (dx != nullptr) {
-      if (ds.on) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dz[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (zz[j] - mean) * rstd;
+        dz[j] = rstd * (d[j] * g[c * 8 + j] - s1 - xh * s2);
       }
+      if (dres != nullptr) {
+        float o8[8];
+        if (has_in) {
+          unpack8(cr[c], o8);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) acc_x[i] += dz[i];
-      store_row_bf16<NCH>(dx + (long long)row * H, lane, dz);
+          for (int j = 0; j < 8; ++j) o8[j] += dz[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = dz[j];
+        }
+        *reinterpret_cast<uint4*>(dres + o + c * 256) = pack8(o8);
+      }
+      if (dx != nullptr) {
+        if (ds.on) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_x[c * 8 + j] += dz[j];
+        *reinterpret_cast<uint4*>(dx + o + c * 256) = pack8(dz);
+      }
     }
   }
-  float* slab = slab_all + (threadIdx.x >> 5) * (3 * H) + lane;
+  float* slab = slab_all + warp * (3 * H) + lane;       // value index major, lane minor: 32 consecutive banks per store
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     slab[(0 * NV + i) * 32] = acc_g[i];
@@ -258,165 +232,71 @@ __global__ void __launch_bounds__(256, OCC2 ? 2 : 1) ln_bwd_kernel_v2(const __nv
     slab[(2 * NV + i) * 32] = acc_x[i];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 3 * H; idx += blockDim.x) {       // fold the warp-private slabs, one global red per column and CTA
-    float v = slab_all[idx];
-    for (int w = 1; w < wpb; ++w) v += slab_all[w * 3 * H + idx];
-    const int a = idx / H, r = idx % H;
-    const int i = r >> 5, l = r & 31;                         // value i of lane l  ->  column (i / 8) * 256 + l * 8 + (i % 8)
-    const int col = (i >> 3) * 256 + l * 8 + (i & 7);
+  // fold the warp-private slabs: thread t owns 4 consecutive COLUMNS of one accumulator -> one vector red per thread and pass
+  for (int q = threadIdx.x; q < 3 * H / 4; q += blockDim.x) {
+    const int a = q / (H / 4), col = (q % (H / 4)) * 4;
     float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
-    if (dst) atomicAdd(dst + col, v);
+    if (dst == nullptr) continue;
+    // column col + k  <-  value i = (col / 256) * 8 + (col % 8) + k of lane l = (col % 256) / 8
+    const int i0 = (col >> 8) * 8 + (col & 7), l = (col & 255) >> 3;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < wpb; ++w) {
+      const float* sl = slab_all + w * (3 * H) + (a * NV + i0) * 32 + l;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += sl[k * 32];
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + col), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
   }
 }
-
-// EXPERIMENTAL variant 3: as v2, but the three column-sum accumulators are not kept in registers across rows (72 registers per lane,
-// the reason the kernels above need ~240 registers and run one CTA = 8 warps per SM).  Every warp owns a private [3][NCH*8][32] slab
-// in dynamic shared memory (lane-minor: 32 consecutive banks per access, no other warp touches it) and adds its row's contributions
-// with plain load / add / store -- fp32 shared-memory atomics compile to a compare-and-swap spin loop on sm_100 (ATOMS.CAST.SPIN), so
-// they are avoided.  The slabs are folded by the CTA at the end.  Aim: <= 128 registers without spills -> 2 CTAs per SM.
-template <int NCH>
-__global__ void __launch_bounds__(256, 2) ln_bwd_kernel_v3(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
-                                                           const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                           const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
-                                                           __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
-                                                           float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
-  pdl_grid_sync();
-  constexpr int H = NCH * 256;
-  constexpr int NV = NCH * 8;
-  extern __shared__ float slab_all[];                 // [warps][3][NV][32]
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const DropState ds = drop_init(dc);
-  for (int i = threadIdx.x; i < wpb * 3 * H; i += blockDim.x) slab_all[i] = 0.f;
-  __syncthreads();
-  float* slab = slab_all + (threadIdx.x >> 5) * (3 * H) + lane;      // element (a, i) of this lane: slab[(a * NV + i) * 32]
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
-    float d[NV], zz[NV], o[NV];
-    load_row_bf16<NCH>(dy + (long long)row * H, lane, d);
-    load_row_bf16<NCH>(z + (long long)row * H, lane, zz);
-    const bool has_in = dres != nullptr && dres_in != nullptr;
-    if (has_in) load_row_bf16<NCH>(dres_in + (long long)row * H, lane, o);
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const float4 ga = *reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8);
-      const float4 gb = *reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8 + 4);
-      const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = c * 8 + j;
-        const float xh = (zz[i] - mean) * rstd;
-        const float gd = d[i] * gg[j];
-        slab[(0 * NV + i) * 32] += d[i] * xh;
-        slab[(1 * NV + i) * 32] += d[i];
-        s1 += gd;
-        s2 += gd * xh;
-        zz[i] = xh;
-        d[i] = gd;
-      }
-    }
-    s1 = warp_sum(s1) * (1.0f / H);
-    s2 = warp_sum(s2) * (1.0f / H);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) d[i] = rstd * (d[i] - s1 - zz[i] * s2);      // d <- dz
-    if (dres != nullptr) {
-      if (has_in) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) o[i] += d[i];
-        store_row_bf16<NCH>(dres + (long long)row * H, lane, o);
-      } else {
-        store_row_bf16<NCH>(dres + (long long)row * H, lane, d);
-      }
-    }
-    if (dx != nullptr) {
-      if (ds.on) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[c * 8 + j] *= drop_mult(ds, (unsigned long long)row * H + c * 256 + lane * 8 + j);
-      }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) slab[(2 * NV + i) * 32] += d[i];
-      store_row_bf16<NCH>(dx + (long long)row * H, lane, d);
-    }
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 3 * H; idx += blockDim.x) {       // fold the warp-private slabs, one global red per column and CTA
-    float v = slab_all[idx];
-    for (int w = 1; w < wpb; ++w) v += slab_all[w * 3 * H + idx];
-    const int a = idx / H, r = idx % H;
-    const int i = r >> 5, l = r & 31;
-    const int col = (i >> 3) * 256 + l * 8 + (i & 7);
-    float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
-    if (dst) atomicAdd(dst + col, v);
-  }
-}
-
-static int g_ln_variant = 0;       // hamt_ln_set_variant: 0 = ln_bwd_kernel (default), 1 / 2 = ln_bwd_kernel_v2 with 1 / 2 CTAs per SM, 3 = ln_bwd_kernel_v3 (all experimental)
-void ln_set_variant(int v) { g_ln_variant = v; }
 
 static int grid_for_rows(int M, int wpb, int max_ctas) {
   int g = (M + wpb - 1) / wpb;
   return g < max_ctas ? (g < 1 ? 1 : g) : max_ctas;
 }
 
-int ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* z_out, float* mean, float* rstd, int M,
-           int H, float eps, DropArgs drop, cudaStream_t st) {
+int ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
+           float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st) {
   HAMT_REQUIRE(H == 512 || H == 768 || H == 1024, "ln_fwd: hidden size must be 512/768/1024");
+  HAMT_REQUIRE(res == nullptr || res32 == nullptr, "ln_fwd: the residual comes either as bf16 or as fp32, not both");
+  HAMT_REQUIRE((((uintptr_t)res32 | (uintptr_t)y32) & 15) == 0, "ln_fwd: fp32 residual / output must be 16-byte aligned");
   if (M <= 0) return 0;
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
   const int grid = grid_for_rows(M, 8, 148 * 8);
   auto X = (const __nv_bfloat16*)x; auto R = (const __nv_bfloat16*)res; auto Y = (__nv_bfloat16*)y; auto Z = (__nv_bfloat16*)z_out;
-  if (H == 768) launch_pdl(ln_fwd_kernel<3>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
-  else if (H == 512) launch_pdl(ln_fwd_kernel<2>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
-  else launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, X, R, gamma, beta, Y, Z, mean, rstd, M, eps, dc);
+  if (H == 768) launch_pdl(ln_fwd_kernel<3>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
+  else if (H == 512) launch_pdl(ln_fwd_kernel<2>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
+  else launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
   return check_launch("ln_fwd_kernel");
 }
 
 int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
            float* dgamma, float* dbeta, float* dbias, int M, int H, DropArgs drop, cudaStream_t st) {
   HAMT_REQUIRE(H == 512 || H == 768 || H == 1024, "ln_bwd: hidden size must be 512/768/1024");
+  HAMT_REQUIRE((((uintptr_t)dgamma | (uintptr_t)dbeta | (uintptr_t)dbias) & 15) == 0, "ln_bwd: column-sum outputs must be 16-byte aligned");
   if (M <= 0) return 0;
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
-  const int grid = grid_for_rows(M, 8 * 4, 148 * 2);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = grid_for_rows(M, 8, sms);           // one wave: the kernel holds one CTA per SM
+  const size_t smem = (size_t)8 * 3 * H * sizeof(float);   // 8 warps x [3][H] fp32: 72 KB at H = 768
   auto DY = (const __nv_bfloat16*)dy; auto Z = (const __nv_bfloat16*)z; auto DRI = (const __nv_bfloat16*)dres_in;
   auto DX = (__nv_bfloat16*)dx; auto DR = (__nv_bfloat16*)dres;
-  if (g_ln_variant == 3) {
-    const size_t smem = (size_t)8 * 3 * H * sizeof(float);           // 8 warps x [3][H] fp32: 72 KB at H = 768
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 512 * 4);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4);
-      if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
-      attr_set = true;
-    }
-    if (H == 768) launch_pdl(ln_bwd_kernel_v3<3>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-    else if (H == 512) launch_pdl(ln_bwd_kernel_v3<2>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-    else launch_pdl(ln_bwd_kernel_v3<4>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-    return check_launch("ln_bwd_kernel_v3");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 512 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    attr_set = true;
   }
-  if (g_ln_variant == 1 || g_ln_variant == 2) {
-    const size_t smem2 = (size_t)8 * 3 * H * sizeof(float);
-#define HAMT_LNV2(NCH_)                                                                                                        \
-  {                                                                                                                            \
-    static bool set_ = false;                                                                                                  \
-    if (!set_) {                                                                                                               \
-      cudaFuncSetAttribute(ln_bwd_kernel_v2<NCH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * NCH_ * 256 * 4); \
-      cudaFuncSetAttribute(ln_bwd_kernel_v2<NCH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * NCH_ * 256 * 4);\
-      set_ = true;                                                                                                             \
-    }                                                                                                                          \
-    if (g_ln_variant == 2) launch_pdl(ln_bwd_kernel_v2<NCH_, true>, grid, 256, smem2, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc); \
-    else launch_pdl(ln_bwd_kernel_v2<NCH_, false>, grid, 256, smem2, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);                  \
-  }
-    if (H == 768) HAMT_LNV2(3) else if (H == 512) HAMT_LNV2(2) else HAMT_LNV2(4)
-#undef HAMT_LNV2
-    return check_launch("ln_bwd_kernel_v2");
-  }
-  if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else launch_pdl(ln_bwd_kernel<4>, grid, 256, 0, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  else launch_pdl(ln_bwd_kernel<4>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
   return check_launch("ln_bwd_kernel");
 }
 

@@ -89,10 +89,14 @@ class FeatureStore:
                 raise IndexError("FeatureStore: view index out of range")
 
     # -- device side: indices -> model inputs ------------------------------------------------------------------------
-    def assemble_history(self, hist_pano: torch.Tensor, hist_view: torch.Tensor, with_pano: bool = True, with_probs: bool = False) -> Dict:
+    def assemble_history(self, hist_pano: torch.Tensor, hist_view: torch.Tensor, with_pano: bool = True, with_probs: bool = False,
+                         mrc_mask: Optional[torch.Tensor] = None) -> Dict:
         """hist_pano / hist_view: int64 [B, T]; -1 = padding (step >= the sample's history length).  Returns the reference's batch
         entries `hist_img_fts` [B,T,D], `hist_pano_img_fts` [B,T,36,D], `hist_pano_ang_fts` [B,T,36,A] (features in bf16) and, with
-        with_probs, `hist_img_probs` [B,T,P] fp32.  T == 0 -> every entry is None (r2r_tasks.py:360-366)."""
+        with_probs, `hist_img_probs` [B,T,P] fp32.  T == 0 -> every entry is None (r2r_tasks.py:360-366).
+        mrc_mask (bool [B,T], optional): the MRC augmentation (`_mask_img_feat` / `_mask_pano_img_feat`, r2r_tasks.py:183-190) zeroes
+        ONLY the image features of the masked steps (`hist_img_fts`, `hist_pano_img_fts`) and keeps their angle features and their
+        class probabilities (the prediction targets)."""
         self._check(hist_pano, hist_view)
         B, T = hist_pano.shape
         keys = ["hist_img_fts"] + (["hist_pano_img_fts", "hist_pano_ang_fts"] if with_pano else []) + (["hist_img_probs"] if with_probs else [])
@@ -103,9 +107,15 @@ class FeatureStore:
         valid = (pano >= 0) & (view >= 0)
         base = pano * N_VIEWS
         row = torch.where(valid, base + view, torch.full_like(base, -1))
-        out = {"hist_img_fts": ops.gather_rows_pad(self.table, row.reshape(-1).contiguous()).view(B, T, self.D)}
+        shown = valid
+        if mrc_mask is not None:
+            if mrc_mask.shape != hist_pano.shape:
+                raise ValueError("FeatureStore: mrc_mask must be [B, T]")
+            shown = valid & ~mrc_mask.to(self.device, non_blocking=True).bool()
+        img_row = torch.where(shown, row, torch.full_like(row, -1))
+        out = {"hist_img_fts": ops.gather_rows_pad(self.table, img_row.reshape(-1).contiguous()).view(B, T, self.D)}
         if with_pano:
-            rows36 = torch.where(valid[..., None], base[..., None] + self._views, torch.full((1,), -1, dtype=torch.int64, device=self.device))
+            rows36 = torch.where(shown[..., None], base[..., None] + self._views, torch.full((1,), -1, dtype=torch.int64, device=self.device))
             out["hist_pano_img_fts"] = ops.gather_rows_pad(self.table, rows36.reshape(-1).contiguous()).view(B, T, N_VIEWS, self.D)
             ang = self.angle_table[view.clamp(min=0)]                                    # [B,T,36,A]
             out["hist_pano_ang_fts"] = ang * valid[..., None, None].to(ang.dtype)

@@ -19,13 +19,24 @@ from . import ops
 from .arena import ParamArena
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _new32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 twin of a bf16 activation buffer: the residual stream is carried in full precision between LayerNorms (ln_fwd)."""
+    return torch.empty(x.shape, dtype=F32, device=x.device)
+
+
+def _as32(x16: torch.Tensor, x32: Optional[torch.Tensor]) -> torch.Tensor:
+    return x32 if x32 is not None else x16.detach().float()
 
 
 class Run:
     """Per-forward context: arena, mode, dropout probabilities and the dropout call-site counter."""
 
-    def __init__(self, arena: ParamArena, training: bool, heads: int, eps: float):
+    def __init__(self, arena: ParamArena, training: bool, heads: int, eps: float, seed=None):
         self.arena = arena
+        self.seed = seed            # this forward's private dropout seed cell (arena.run_seed()); None in eval
         self.training = training
         self.heads = heads
         self.eps = eps
@@ -49,7 +60,7 @@ class Run:
         if not self.training or p <= 0.0:
             return ops.NO_DROP
         self._site += 1
-        return ops.Drop(self.arena.seed, self._site, p)
+        return ops.Drop(self.seed if self.seed is not None else self.arena.seed, self._site, p)
 
 
 def _wgrad(A: ParamArena, dy: torch.Tensor, x: torch.Tensor, weight):
@@ -70,7 +81,8 @@ def _qkv_params(att):
     return [att.query.weight, att.key.weight, att.value.weight], [att.query.bias, att.key.bias, att.value.bias]
 
 
-def attn_block_fwd(run: Run, x, B: int, S: int, mask, att, out_mod, y_out=None):
+def attn_block_fwd(run: Run, x, B: int, S: int, mask, att, out_mod, y_out=None, x32=None, y32_out=None):
+    """x32: fp32 twin of x (residual), or None -> the bf16 x is the residual.  Returns (y, y32, saved)."""
     A, H = run.arena, x.shape[1]
     ws, bs = _qkv_params(att)
     qkv = ops.gemm(x, A.fused_w16(ws), bias=A.fused_param(bs))
@@ -79,9 +91,10 @@ def attn_block_fwd(run: Run, x, B: int, S: int, mask, att, out_mod, y_out=None):
     t = ops.gemm(ctx, A.w16(out_mod.dense.weight), bias=out_mod.dense.bias)
     d_hid = run.drop(out_mod.dropout)
     ln = out_mod.LayerNorm
-    y, z, mean, rstd = ops.ln_fwd(t, x, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out)
+    y32 = _new32(x) if y32_out is None else y32_out
+    y, z, mean, rstd = ops.ln_fwd(t, x if x32 is None else x32, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out, out32=y32)
     saved = (x, qkv, ctx, lse, z, mean, rstd, d_attn, d_hid, mask, B, S) if run.save else None
-    return y, saved
+    return y, y32, saved
 
 
 def attn_block_bwd(run: Run, dy, saved, att, out_mod, dx_out=None):
@@ -105,7 +118,7 @@ def attn_block_bwd(run: Run, dy, saved, att, out_mod, dx_out=None):
 # ------------------------------------------------------------------------------------------------
 # feed-forward block
 # ------------------------------------------------------------------------------------------------
-def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None):
+def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None, x32=None, y32_out=None):
     A = run.arena
     w1, w2 = inter.dense.weight, out_mod.dense.weight
     if run.save:
@@ -117,9 +130,10 @@ def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None):
     t = ops.gemm(a, A.w16(w2), bias=out_mod.dense.bias)
     d_hid = run.drop(out_mod.dropout)
     ln = out_mod.LayerNorm
-    y, z, mean, rstd = ops.ln_fwd(t, x, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out)
+    y32 = _new32(x) if y32_out is None else y32_out
+    y, z, mean, rstd = ops.ln_fwd(t, x if x32 is None else x32, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y_out, out32=y32)
     saved = (x, h, a, z, mean, rstd, d_hid) if run.save else None
-    return y, saved
+    return y, y32, saved
 
 
 def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
@@ -140,7 +154,7 @@ def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
 # ------------------------------------------------------------------------------------------------
 # cross attention, both directions, shared weights (rows [0:ML] = language, [ML:] = vision)
 # ------------------------------------------------------------------------------------------------
-def cross_block_fwd(run: Run, xcat, B: int, L: int, V: int, lang_mask, visn_mask, xatt, lang_ca: bool = True):
+def cross_block_fwd(run: Run, xcat, B: int, L: int, V: int, lang_mask, visn_mask, xatt, lang_ca: bool = True, xcat32=None):
     A, H = run.arena, xcat.shape[1]
     ML = B * L
     ws, bs = _qkv_params(xatt.att)
@@ -153,17 +167,20 @@ def cross_block_fwd(run: Run, xcat, B: int, L: int, V: int, lang_mask, visn_mask
     _, lse_v = ops.attn_fwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v, need_lse=run.save, out=ctx[ML:])
     ln, dense = xatt.output.LayerNorm, xatt.output.dense
     d_hid = run.drop(xatt.output.dropout)
+    y32 = _new32(xcat)
+    res = xcat if xcat32 is None else xcat32
     if lang_ca:
         t = ops.gemm(ctx, A.w16(dense.weight), bias=dense.bias)
-        y, z, mean, rstd = ops.ln_fwd(t, xcat, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save)
+        y, z, mean, rstd = ops.ln_fwd(t, res, ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out32=y32)
     else:
         # finetune no_lang_ca (vilmodel_cmt.py:379-384): language rows pass through unchanged
         y = torch.empty_like(xcat)
         y[:ML].copy_(xcat[:ML])
+        y32[:ML].copy_(res[:ML])
         t = ops.gemm(ctx[ML:], A.w16(dense.weight), bias=dense.bias)
-        _, z, mean, rstd = ops.ln_fwd(t, xcat[ML:], ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y[ML:])
+        _, z, mean, rstd = ops.ln_fwd(t, res[ML:], ln.weight, ln.bias, run.eps, d_hid, save_z=run.save, out=y[ML:], out32=y32[ML:])
     saved = (xcat, qkv, ctx, lse_l, lse_v, z, mean, rstd, d_att_l, d_att_v, d_hid, lang_mask, visn_mask, B, L, V, lang_ca) if run.save else None
-    return y, saved
+    return y, y32, saved
 
 
 def cross_block_bwd(run: Run, dy, saved, xatt):
@@ -211,47 +228,53 @@ class BertLayerFn(torch.autograd.Function):
     """BertLayer (vilmodel.py:188-201) on rows x [B*S, H]."""
 
     @staticmethod
-    def forward(ctx, anchor, x, run: Run, layer, B: int, S: int, mask):
-        y1, s1 = attn_block_fwd(run, x, B, S, mask, layer.attention.self, layer.attention.output)
-        y2, s2 = ffn_block_fwd(run, y1, layer.intermediate, layer.output)
+    def forward(ctx, anchor, x, x32, run: Run, layer, B: int, S: int, mask):
+        """Returns (y bf16, y32 fp32 twin -- not differentiable: the whole gradient travels through y)."""
+        y1, y1_32, s1 = attn_block_fwd(run, x, B, S, mask, layer.attention.self, layer.attention.output, x32=x32)
+        y2, y2_32, s2 = ffn_block_fwd(run, y1, layer.intermediate, layer.output, x32=y1_32)
         ctx.run, ctx.layer, ctx.s1, ctx.s2 = run, layer, s1, s2
         run.used(layer)
-        return y2
+        ctx.mark_non_differentiable(y2_32)
+        return y2, y2_32
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy32=None):
         run, layer = ctx.run, ctx.layer
         dy = _as_bf16_2d(dy, ctx.s2[0])
         d1 = ffn_block_bwd(run, dy, ctx.s2, layer.intermediate, layer.output)
         dx = attn_block_bwd(run, d1, ctx.s1, layer.attention.self, layer.attention.output)
         ctx.s1 = ctx.s2 = None
         run.done(layer)
-        return None, dx, None, None, None, None, None
+        return None, dx, None, None, None, None, None, None
 
 
 class XLayerFn(torch.autograd.Function):
     """LXRTXLayer (vilmodel.py:362-412) on the joint buffer xcat = [language rows ; vision rows]."""
 
     @staticmethod
-    def forward(ctx, anchor, xcat, run: Run, layer, B: int, L: int, V: int, lang_mask, visn_mask, lang_ca: bool):
+    def forward(ctx, anchor, xcat, xcat32, run: Run, layer, B: int, L: int, V: int, lang_mask, visn_mask, lang_ca: bool):
         ML = B * L
-        y0, s0 = cross_block_fwd(run, xcat, B, L, V, lang_mask, visn_mask, layer.visual_attention, lang_ca)
-        y1 = torch.empty_like(y0)
-        out = torch.empty_like(y0)
+        y0, y0_32, s0 = cross_block_fwd(run, xcat, B, L, V, lang_mask, visn_mask, layer.visual_attention, lang_ca, xcat32=xcat32)
+        y1, y1_32 = torch.empty_like(y0), _new32(y0)
+        out, out32 = torch.empty_like(y0), _new32(y0)
         if lang_ca:
-            _, sl = attn_block_fwd(run, y0[:ML], B, L, lang_mask, layer.lang_self_att.self, layer.lang_self_att.output, y_out=y1[:ML])
-            _, fl = ffn_block_fwd(run, y1[:ML], layer.lang_inter, layer.lang_output, y_out=out[:ML])
+            _, _, sl = attn_block_fwd(run, y0[:ML], B, L, lang_mask, layer.lang_self_att.self, layer.lang_self_att.output, y_out=y1[:ML],
+                                      x32=y0_32[:ML], y32_out=y1_32[:ML])
+            _, _, fl = ffn_block_fwd(run, y1[:ML], layer.lang_inter, layer.lang_output, y_out=out[:ML], x32=y1_32[:ML], y32_out=out32[:ML])
         else:
             sl = fl = None
             out[:ML].copy_(y0[:ML])
-        _, sv = attn_block_fwd(run, y0[ML:], B, V, visn_mask, layer.visn_self_att.self, layer.visn_self_att.output, y_out=y1[ML:])
-        _, fv = ffn_block_fwd(run, y1[ML:], layer.visn_inter, layer.visn_output, y_out=out[ML:])
+            out32[:ML].copy_(y0_32[:ML])
+        _, _, sv = attn_block_fwd(run, y0[ML:], B, V, visn_mask, layer.visn_self_att.self, layer.visn_self_att.output, y_out=y1[ML:],
+                                  x32=y0_32[ML:], y32_out=y1_32[ML:])
+        _, _, fv = ffn_block_fwd(run, y1[ML:], layer.visn_inter, layer.visn_output, y_out=out[ML:], x32=y1_32[ML:], y32_out=out32[ML:])
         ctx.run, ctx.layer, ctx.saved, ctx.ML, ctx.lang_ca = run, layer, (s0, sl, fl, sv, fv), ML, lang_ca
         run.used(layer)
-        return out
+        ctx.mark_non_differentiable(out32)
+        return out, out32
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dout32=None):
         run, layer, ML = ctx.run, ctx.layer, ctx.ML
         s0, sl, fl, sv, fv = ctx.saved
         dout = _as_bf16_2d(dout, s0[0])
@@ -267,7 +290,7 @@ class XLayerFn(torch.autograd.Function):
         dx = cross_block_bwd(run, d0, s0, layer.visual_attention)
         ctx.saved = None
         run.done(layer)
-        return (None, dx) + (None,) * 8
+        return (None, dx) + (None,) * 9
 
 
 class LangSelfFn(torch.autograd.Function):
@@ -275,9 +298,9 @@ class LangSelfFn(torch.autograd.Function):
     no_lang_ca (vilmodel_cmt.py:645-652)."""
 
     @staticmethod
-    def forward(ctx, anchor, x, run: Run, layer, B: int, L: int, mask):
-        y1, s1 = attn_block_fwd(run, x, B, L, mask, layer.lang_self_att.self, layer.lang_self_att.output)
-        y2, s2 = ffn_block_fwd(run, y1, layer.lang_inter, layer.lang_output)
+    def forward(ctx, anchor, x, x32, run: Run, layer, B: int, L: int, mask):
+        y1, y1_32, s1 = attn_block_fwd(run, x, B, L, mask, layer.lang_self_att.self, layer.lang_self_att.output, x32=x32)
+        y2, _, s2 = ffn_block_fwd(run, y1, layer.lang_inter, layer.lang_output, x32=y1_32)
         ctx.run, ctx.layer, ctx.s1, ctx.s2 = run, layer, s1, s2
         return y2
 
@@ -287,7 +310,7 @@ class LangSelfFn(torch.autograd.Function):
         dy = _as_bf16_2d(dy, ctx.s2[0])
         d1 = ffn_block_bwd(run, dy, ctx.s2, layer.lang_inter, layer.lang_output)
         dx = attn_block_bwd(run, d1, ctx.s1, layer.lang_self_att.self, layer.lang_self_att.output)
-        return None, dx, None, None, None, None, None
+        return None, dx, None, None, None, None, None, None
 
 
 class LinearFn(torch.autograd.Function):
@@ -481,9 +504,9 @@ class RowLNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, x, run: Run, ln, drop_mod):
         d = run.drop(drop_mod)
-        # fp32 input carried as a bf16 (hi, lo) pair through the kernel's residual slot: hi + lo is summed in fp32
+        # fp32 input: the bf16 part goes through the kernel's x slot, the remainder through its fp32 residual slot (summed in fp32)
         x16 = x.to(BF16).contiguous()
-        lo = (x - x16.float()).to(BF16).contiguous()
+        lo = (x - x16.float()).contiguous()
         y, z, mean, rstd = ops.ln_fwd(x16, lo, ln.weight, ln.bias, run.eps, save_z=True, inplace_z=True)
         # dropout AFTER the norm: applied as ln_fwd(dropout(.)) is wrong here, so do it with the streaming kernel trick:
         ctx.run, ctx.ln, ctx.saved, ctx.d = run, ln, (z, mean, rstd), d

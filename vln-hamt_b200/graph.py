@@ -70,13 +70,20 @@ def _signature(task, batch):
 
 
 class GraphedStep:
-    """One captured `loss = model(batch, task); loss.mean().backward()` for a fixed batch signature."""
+    """One captured `loss = model(batch, task); loss.mean().backward()` for a fixed batch signature.
+
+    The captured body holds ONLY the forward + backward (+ gradient exchange) launches.  What depends on the training
+    loop's state runs eagerly in `__call__` before the replay: the bf16 weight-shadow cast (skipped when the fused
+    optimizer refreshed it), the gradient reset (skipped with `accumulate=True`: gradient_accumulation_steps > 1 in the
+    reference loop, main_r2r.py:243-249) and the dropout-seed advance."""
 
     _pools: Dict[int, object] = {}
 
     def __init__(self, model, task: str, batch: Dict, post_backward=None, warmup: int = 2, bwd_sm_limit: int = 0):
         self.model, self.task = model, task
         dev = next(model.parameters()).device
+        arena = model.arena()
+        arena.ensure()
         # static inputs of the captured step: one packed device blob (loader.Layout), so a packed batch arrives with ONE copy
         self.layout = Layout(batch)
         self.blob = torch.empty(self.layout.nbytes, dtype=torch.uint8, device=dev)
@@ -100,32 +107,63 @@ class GraphedStep:
                 post_backward()
             return loss
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                model.zero_grad(set_to_none=True)
-                body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        model.zero_grad(set_to_none=True)          # the captured step starts by zeroing the flat gradient buffer
-        pool = GraphedStep._pools.get(id(model))
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        # thread_local: the NCCL watchdog thread (data-parallel runs) polls CUDA events while we capture
-        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode="thread_local"):
-            self.loss = body()
-        self.native_launches = _lib.launch_count() - n0
+        # A capture may happen in the middle of training (first batch of a new signature): the warm-up passes must not disturb
+        # gradients that are being accumulated, nor the dropout-seed sequence.
+        prev_touched, prev_sentinel = list(arena._touched), arena._sentinel
+        grad_backup = arena.flat_grad.clone() if prev_touched else None
+        arena.step_begin(True, zero_grads=False)       # a valid bf16 shadow for the warm-up passes
+        for p in prev_touched:                         # so that what is attached below is exactly this task's touched set
+            p.grad = None
+        arena._touched, arena._sentinel = [], None
+        arena.external_prologue = True
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            pool = GraphedStep._pools.get(id(model))
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            # thread_local: the NCCL watchdog thread (data-parallel runs) polls CUDA events while we capture
+            with torch.cuda.graph(self.graph, pool=pool, capture_error_mode="thread_local"):
+                self.loss = body()
+            self.native_launches = _lib.launch_count() - n0
+        finally:
+            arena.external_prologue = False
         if pool is None:
             GraphedStep._pools[id(model)] = self.graph.pool()
         # after a replay the gradients of exactly the parameters this task touches are valid
-        self.touched = list(model.arena()._touched)
+        self.touched = list(arena._touched)
         self.touched_ids = {id(p) for p in self.touched}
+        # restore the pre-capture gradient state
+        for p in arena.params:
+            p.grad = None
+        if grad_backup is not None:
+            arena.flat_grad.copy_(grad_backup)
+            for p in prev_touched:
+                o = arena.offsets[id(p)]
+                p.grad = arena.flat_grad[o:o + p.numel()].view(p.shape)
+            arena._touched, arena._sentinel = prev_touched, prev_sentinel
+        else:
+            arena.flat_grad.zero_()
+            arena._touched, arena._sentinel = [], None
 
     def matches(self, task, batch) -> bool:
         return _signature(task, batch) == self.signature
 
-    def __call__(self, batch: Dict) -> torch.Tensor:
+    def __call__(self, batch: Dict, accumulate: bool = False) -> torch.Tensor:
+        arena = self.model.arena()
+        # ---- eager prologue (never captured): shadow cast, gradient reset, seed advance ----
+        arena.step_begin(True, zero_grads=False)
+        keep = []
+        if accumulate:
+            keep = [p for p in arena._touched if p.grad is not None]
+        elif arena._touched:
+            arena.flat_grad.zero_()
+        arena.next_seed()
         packed = batch.get("_packed")
         if packed is not None and packed.layout.key == self.layout.key:
             self.blob.copy_(packed.dev, non_blocking=True)           # one device-to-device copy of the whole batch
@@ -133,17 +171,18 @@ class GraphedStep:
             for path, t in flatten(batch):
                 self._static_flat[path].copy_(t, non_blocking=True)
         self.graph.replay()
-        arena = self.model.arena()
-        # restore the host-side gradient bookkeeping of this task (graphs of other tasks may have run in between)
+        # host-side gradient bookkeeping of this task (graphs of other tasks may have run in between)
+        keep_ids = {id(p) for p in keep}
         for p in arena._touched:
-            if id(p) not in self.touched_ids:
+            if id(p) not in self.touched_ids and id(p) not in keep_ids:
                 p.grad = None
-        for p in self.touched:
+        now = list(self.touched) + [p for p in keep if id(p) not in self.touched_ids]
+        for p in now:
             if p.grad is None:
                 o = arena.offsets[id(p)]
                 p.grad = arena.flat_grad[o:o + p.numel()].view(p.shape)
-        arena._touched = list(self.touched)
-        arena._sentinel = self.touched[0] if self.touched else None
+        arena._touched = now
+        arena._sentinel = now[0] if now else None
         return self.loss
 
 
@@ -153,10 +192,10 @@ class GraphedTrainer:
     def __init__(self, model, post_backward=None, bwd_sm_limit: int = 0):
         self.model, self.post_backward, self.steps, self.bwd_sm_limit = model, post_backward, {}, bwd_sm_limit
 
-    def step(self, task: str, batch: Dict) -> torch.Tensor:
+    def step(self, task: str, batch: Dict, accumulate: bool = False) -> torch.Tensor:
         sig = _signature(task, batch)
         st = self.steps.get(sig)
         if st is None:
             st = GraphedStep(self.model, task, batch, self.post_backward, bwd_sm_limit=self.bwd_sm_limit)
             self.steps[sig] = st
-        return st(batch)
+        return st(batch, accumulate=accumulate)

@@ -83,16 +83,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool = True, inplace_z: bool = True, out=None):
-    """y = LN(dropout(x) + res).  Returns (y, z, mean, rstd); z aliases x when inplace_z."""
+def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool = True, inplace_z: bool = True, out=None, out32=None):
+    """y = LN(dropout(x) + res).  Returns (y, z, mean, rstd); z aliases x when inplace_z.  `res` may be bf16 or fp32 (the
+    full-precision residual stream); `out32` (fp32 [M,H]) additionally receives the un-rounded y for the next residual add."""
     M, H = x.shape
     y = torch.empty_like(x) if out is None else out
+    res16 = res if (res is not None and res.dtype == BF16) else None
+    res32 = res if (res is not None and res.dtype == F32) else None
+    if res is not None and (res.shape != x.shape or res.stride(1) != 1 or res.stride(0) != H):
+        raise ValueError("ln_fwd: the residual must be a contiguous [M, H] tensor")
+    if out32 is not None and (out32.dtype != F32 or out32.shape != x.shape or out32.stride(0) != H):
+        raise ValueError("ln_fwd: out32 must be contiguous fp32 [M, H]")
     z = (x if inplace_z else torch.empty_like(x)) if save_z else None
     mean = torch.empty(M, dtype=F32, device=x.device) if save_z else None
     rstd = torch.empty(M, dtype=F32, device=x.device) if save_z else None
     sp, site, p = drop.args
-    rc = _lib.load().hamt_ln_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(z), _ptr(mean), _ptr(rstd), M, H,
-                                 eps, sp, site, p, _stream())
+    rc = _lib.load().hamt_ln_fwd(x.data_ptr(), _ptr(res16), _ptr(res32), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(out32), _ptr(z),
+                                 _ptr(mean), _ptr(rstd), M, H, eps, sp, site, p, _stream())
     _lib.check(rc, "ln_fwd")
     return y, z, mean, rstd
 

@@ -163,6 +163,54 @@ class AdamW:
         return out
 
 
+    # -------------------------------------------------------------------------------------------------------------
+    def state_dict(self) -> Dict:
+        """torch.optim.Optimizer.state_dict() layout ({'state': {index: {...}}, 'param_groups': [{..., 'params': [indices]}]}), what
+        the reference's checkpointing stores (pretrain_src/utils/save.py:42 `optimizer.state_dict()`; finetune agent_cmt.py:616).
+        Parameters that were never updated (their task never ran) have no entry, like the reference's lazily created state."""
+        steps = self.seg_step.cpu().tolist()
+        index, groups, i0 = {}, [], 0
+        for g in self.param_groups:
+            ids = list(range(i0, i0 + len(g["params"])))
+            for i, p in zip(ids, g["params"]):
+                index[id(p)] = i
+            i0 += len(g["params"])
+            groups.append({**{k: v for k, v in g.items() if k != "params"}, "params": ids})
+        state = {}
+        for s, p in enumerate(self.seg_params):
+            if steps[s] == 0:
+                continue
+            o = self.arena.offsets[id(p)]
+            state[index[id(p)]] = dict(step=steps[s], exp_avg=self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
+                                       exp_avg_sq=self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone())
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: Dict):
+        """Inverse of state_dict(); also accepts a state_dict written by the reference's own AdamW (same layout)."""
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        by_index = {}
+        for g_saved, g in zip(groups, self.param_groups):
+            for k, v in g_saved.items():
+                if k != "params":
+                    g[k] = v
+            for i, p in zip(g_saved["params"], g["params"]):
+                by_index[i] = p
+        seg_of = {id(p): s for s, p in enumerate(self.seg_params)}
+        steps = torch.zeros(self.nseg, dtype=torch.int32)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, st in sd["state"].items():
+            p = by_index[int(i)]
+            o = self.arena.offsets[id(p)]
+            steps[seg_of[id(p)]] = int(st["step"])
+            self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+        self.seg_step.copy_(steps)
+        self._lr_last = None
+
+
 def build_optimizer(model, opts) -> AdamW:
     """misc.py:12-37 for opts.optim == 'adamw' (the shipped recipe, pretrain_r2r.json:24): decay everything except names containing
     'bias', 'LayerNorm.bias', 'LayerNorm.weight'."""

@@ -252,6 +252,10 @@ class HamtPreTrainedModel(nn.Module):
         super().__init__()
         self.config = config
         self._arena: Optional[ParamArena] = None
+        heads, hidden = getattr(config, "num_attention_heads", None), getattr(config, "hidden_size", None)
+        if heads and hidden and (hidden % heads != 0 or hidden // heads != 64):
+            raise ValueError(f"hamt_b200: the attention kernels are built for head_dim 64 (hidden_size {hidden} / num_attention_heads {heads} "
+                             f"= {hidden / heads:g})")
 
     def _init_weights(self, module):
         """BERT init (transformers 4.12.3 BertPreTrainedModel._init_weights): N(0, initializer_range), zero bias, LN = (1, 0)."""
@@ -306,9 +310,11 @@ class HamtPreTrainedModel(nn.Module):
         """Start a forward: refresh the bf16 shadow, attach/zero gradients, advance the dropout seed."""
         arena = self.arena()
         arena.step_begin(self.training and torch.is_grad_enabled())
+        seed = None
         if self.training:
             arena.next_seed()
-        return Fn.Run(arena, self.training, self.config.num_attention_heads, float(self.config.layer_norm_eps))
+            seed = arena.run_seed()
+        return Fn.Run(arena, self.training, self.config.num_attention_heads, float(self.config.layer_norm_eps), seed=seed)
 
 
 def itm_negative_plan(batch_size: int, hist_masks: torch.Tensor, hist_max_len: int, num_neg_trajs: int = 4):
@@ -368,8 +374,9 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         Pd = dict(img_linear=he.pano_img_linear, ang_linear=he.pano_ang_linear, ln_img=he.pano_img_layer_norm, ln_ang=he.pano_ang_layer_norm)
         e = Fn.FeatEmbedFn.apply(run.arena.anchor, None, run, Pd, _feat16(pano_img), pano_ang.reshape(N * P, -1).float().contiguous(), None, None, 1,
                                  drop_mod)
+        e32 = None
         for layer in he.pano_encoder.layer:
-            e = Fn.BertLayerFn.apply(run.arena.anchor, e, run, layer, N, P, None)     # all-zero mask (vilmodel.py:560)
+            e, e32 = Fn.BertLayerFn.apply(run.arena.anchor, e, e32, run, layer, N, P, None)     # all-zero mask (vilmodel.py:560)
         return Fn.MeanPoolFn.apply(e, N, P)
 
     def _hist_cls(self, run, batch_size):
@@ -407,16 +414,19 @@ class NavPreTrainedModel(HamtPreTrainedModel):
 
     # ---- encoder -----------------------------------------------------------------------------
     def _text_layers(self, run, txt, B, L, txt_mask):
+        """-> (txt bf16, txt32: its fp32 twin from the last LayerNorm, or None without layers)."""
+        txt32 = None
         for layer in self.encoder.layer:
-            txt = Fn.BertLayerFn.apply(run.arena.anchor, txt, run, layer, B, L, txt_mask)
+            txt, txt32 = Fn.BertLayerFn.apply(run.arena.anchor, txt, txt32, run, layer, B, L, txt_mask)
         if not self.encoder.update_lang_bert:
             txt = txt.detach()
-        return txt
+        return txt, txt32
 
-    def _x_layers(self, run, txt, visn, B, L, V, txt_mask, visn_mask):
+    def _x_layers(self, run, txt, txt32, visn, B, L, V, txt_mask, visn_mask):
         xcat = torch.cat([txt, visn], 0)
+        xcat32 = torch.cat([Fn._as32(txt, txt32), visn.detach().float()], 0)
         for layer in self.encoder.x_layers:
-            xcat = Fn.XLayerFn.apply(run.arena.anchor, xcat, run, layer, B, L, V, txt_mask, visn_mask, True)
+            xcat, xcat32 = Fn.XLayerFn.apply(run.arena.anchor, xcat, xcat32, run, layer, B, L, V, txt_mask, visn_mask, True)
         return xcat[:B * L], xcat[B * L:]
 
     def forward(self, txt_ids, txt_masks, hist_img_feats, hist_ang_feats, hist_pano_img_feats, hist_pano_ang_feats, hist_masks,
@@ -443,22 +453,22 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         else:
             O, ob, ob_mask = 0, None, None
 
-        txt = self._text_layers(run, txt, B, L, txt_mask)
+        txt, txt32 = self._text_layers(run, txt, B, L, txt_mask)
         if ob is not None and self.encoder.r_layers is not None:
-            o2 = ob.reshape(B * O, H)
+            o2, o32 = ob.reshape(B * O, H), None
             for layer in self.encoder.r_layers:
-                o2 = Fn.BertLayerFn.apply(run.arena.anchor, o2, run, layer, B, O, ob_mask)
+                o2, o32 = Fn.BertLayerFn.apply(run.arena.anchor, o2, o32, run, layer, B, O, ob_mask)
             ob = o2.view(B, O, H)
         if self.encoder.h_layers is not None:
-            h2 = hist.reshape(B * (T + 1), H).contiguous()
+            h2, h32 = hist.reshape(B * (T + 1), H).contiguous(), None
             for layer in self.encoder.h_layers:
-                h2 = Fn.BertLayerFn.apply(run.arena.anchor, h2, run, layer, B, T + 1, hist_mask)
+                h2, h32 = Fn.BertLayerFn.apply(run.arena.anchor, h2, h32, run, layer, B, T + 1, hist_mask)
             hist = h2.view(B, T + 1, H)
         if ob is None:
             visn, visn_mask, V = hist, hist_mask, T + 1
         else:
             visn, visn_mask, V = torch.cat([hist, ob], 1), torch.cat([hist_mask, ob_mask], -1).contiguous(), T + 1 + O
-        txt, visn = self._x_layers(run, txt, visn.reshape(B * V, H), B, L, V, txt_mask, visn_mask)
+        txt, visn = self._x_layers(run, txt, txt32, visn.reshape(B * V, H), B, L, V, txt_mask, visn_mask)
         txt = txt.view(B, L, H)
         visn = visn.view(B, V, H)
         hist_out = visn[:, :T + 1]
@@ -475,8 +485,10 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         L, H = txt_ids.shape[1], self.config.hidden_size
         R = 1 + num_neg_trajs
         txt_mask = _additive_mask(txt_masks)
-        txt = self._text_layers(run, self._text(run, txt_ids), B, L, txt_mask)
+        txt, txt32 = self._text_layers(run, self._text(run, txt_ids), B, L, txt_mask)
         txt = txt.view(B, L, H).repeat(R, 1, 1).reshape(R * B * L, H)
+        if txt32 is not None:
+            txt32 = txt32.view(B, L, H).repeat(R, 1, 1).reshape(R * B * L, H)
         txt_mask_r = txt_mask.repeat(R, 1).contiguous()
 
         hist_mask = _additive_mask(hist_masks)
@@ -493,9 +505,9 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         def h_layers(x):
             if self.encoder.h_layers is None:
                 return x
-            x2 = x.reshape(B * (T + 1), H).contiguous()
+            x2, x32 = x.reshape(B * (T + 1), H).contiguous(), None
             for layer in self.encoder.h_layers:
-                x2 = Fn.BertLayerFn.apply(run.arena.anchor, x2, run, layer, B, T + 1, hist_mask)
+                x2, x32 = Fn.BertLayerFn.apply(run.arena.anchor, x2, x32, run, layer, B, T + 1, hist_mask)
             return x2.view(B, T + 1, H)
 
         dev = txt_ids.device
@@ -514,6 +526,6 @@ class NavPreTrainedModel(HamtPreTrainedModel):
             neg_masks.append(hist_mask)
         visn = torch.cat([hist] + neg_embeds, 0)                                       # [R*B, T+1, H]
         visn_mask = torch.cat([hist_mask] + neg_masks, 0).contiguous()
-        txt, visn = self._x_layers(run, txt, visn.reshape(R * B * (T + 1), H), R * B, L, T + 1, txt_mask_r, visn_mask)
+        txt, visn = self._x_layers(run, txt, txt32, visn.reshape(R * B * (T + 1), H), R * B, L, T + 1, txt_mask_r, visn_mask)
         fused = Fn.MulRowsFn.apply(txt.view(R * B, L, H)[:, 0].contiguous(), visn.view(R * B, T + 1, H)[:, 0].contiguous(), R * B, 1)
         return torch.stack(torch.split(fused, B), 1)                                   # [B, R, H]

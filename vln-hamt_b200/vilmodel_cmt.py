@@ -102,14 +102,15 @@ class NavCMT(HamtPreTrainedModel):
         anchor = run.arena.anchor
         m = _additive_mask(txt_masks)
         txt = Fn.TextEmbedFn.apply(anchor, run, self.embeddings, txt_ids.contiguous())
+        txt32 = None
         for layer in self.encoder.layer:
-            txt = Fn.BertLayerFn.apply(anchor, txt, run, layer, B, L, m)
+            txt, txt32 = Fn.BertLayerFn.apply(anchor, txt, txt32, run, layer, B, L, m)
         if self.config.fix_lang_embedding:
             txt = txt.detach()
         if self.config.no_lang_ca:                      # run the language self-attention stacks of the x-layers
             outs = [txt.view(B, L, H)]
             for layer in self.encoder.x_layers:
-                outs.append(Fn.LangSelfFn.apply(anchor, txt, run, layer, B, L, m).view(B, L, H))
+                outs.append(Fn.LangSelfFn.apply(anchor, txt, txt32, run, layer, B, L, m).view(B, L, H))
             return outs
         return txt.view(B, L, H)
 
@@ -129,8 +130,9 @@ class NavCMT(HamtPreTrainedModel):
                 Pd = dict(img_linear=he.pano_img_linear, ang_linear=he.pano_ang_linear, ln_img=he.pano_img_layer_norm, ln_ang=he.pano_ang_layer_norm)
                 e = Fn.FeatEmbedFn.apply(anchor, None, run, Pd, _feat16(pano_img_feats), pano_ang_feats.reshape(B * P, -1).float().contiguous(), None,
                                          None, 1, he.dropout)                       # finetune drops the pano token embeddings (:583)
+                e32 = None
                 for layer in he.pano_encoder.layer:
-                    e = Fn.BertLayerFn.apply(anchor, e, run, layer, B, P, None)
+                    e, e32 = Fn.BertLayerFn.apply(anchor, e, e32, run, layer, B, P, None)
                 extra = Fn.MeanPoolFn.apply(e, B, P)
             pos_ids = ob_step_ids.reshape(-1).to(hist_img_feats.device)
             if pos_ids.numel() == 1:
@@ -152,9 +154,9 @@ class NavCMT(HamtPreTrainedModel):
         hist_mask = _additive_mask(hist_masks)
         hist = hist_embeds.to(BF16)
         if self.encoder.h_layers is not None:
-            h2 = hist.reshape(B * T1, H).contiguous()
+            h2, h32 = hist.reshape(B * T1, H).contiguous(), None
             for layer in self.encoder.h_layers:
-                h2 = Fn.BertLayerFn.apply(anchor, h2, run, layer, B, T1, hist_mask)
+                h2, h32 = Fn.BertLayerFn.apply(anchor, h2, h32, run, layer, B, T1, hist_mask)
             hist = h2.view(B, T1, H)
         O = ob_img_feats.shape[1]
         ob_mask = _additive_mask(ob_masks)
@@ -164,8 +166,9 @@ class NavCMT(HamtPreTrainedModel):
         ob = Fn.FeatEmbedFn.apply(anchor, None, run, Pd, _feat16(ob_img_feats), ob_ang_feats.reshape(B * O, -1).float().contiguous(),
                                   ob_nav_types.reshape(-1).contiguous(), None, 1, ie.dropout)
         if self.encoder.r_layers is not None:
+            ob32 = None
             for layer in self.encoder.r_layers:
-                ob = Fn.BertLayerFn.apply(anchor, ob, run, layer, B, O, ob_mask)
+                ob, ob32 = Fn.BertLayerFn.apply(anchor, ob, ob32, run, layer, B, O, ob_mask)
         if cfg.fix_obs_embedding:
             ob = ob.detach()
         V = T1 + O
@@ -175,12 +178,15 @@ class NavCMT(HamtPreTrainedModel):
         all_txt = txt_embeds if cfg.no_lang_ca else None
         txt = None if cfg.no_lang_ca else txt_embeds.to(BF16)
         L = (all_txt[0] if cfg.no_lang_ca else txt).shape[1]
+        txt32 = visn32 = None                              # fp32 twins of the two streams between x-layers
         for l, layer in enumerate(self.encoder.x_layers):
             if cfg.no_lang_ca:
-                txt = all_txt[l].to(BF16)
+                txt, txt32 = all_txt[l].to(BF16), None
             xcat = torch.cat([txt.reshape(B * L, H), visn], 0)
-            xcat = Fn.XLayerFn.apply(anchor, xcat, run, layer, B, L, V, txt_mask, visn_mask, not cfg.no_lang_ca)
+            xcat32 = torch.cat([Fn._as32(txt.reshape(B * L, H), txt32), Fn._as32(visn, visn32)], 0)
+            xcat, xcat32 = Fn.XLayerFn.apply(anchor, xcat, xcat32, run, layer, B, L, V, txt_mask, visn_mask, not cfg.no_lang_ca)
             txt, visn = xcat[:B * L].view(B, L, H), xcat[B * L:]
+            txt32, visn32 = xcat32[:B * L], xcat32[B * L:]
         visn = visn.view(B, V, H)
         hist_out, ob_out = visn[:, :T1], visn[:, T1:]
         if cfg.no_lang_ca or cfg.act_pred_token == 'ob':
