@@ -67,6 +67,11 @@ int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* r
                 float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site, float p,
                 void* stream);
 
+/* Attention implementation switch: 0 (default) = the TMA + tcgen05 packed-tile kernels (hamt_attn_tc.cu) wherever the shape fits their
+ * envelope (key length <= 128 after padding to 8) and they win (more than 32 query rows per problem), legacy mma.sync kernels
+ * (hamt_attn.cu) otherwise; 1 = legacy kernels only; 2 = tcgen05 kernels wherever the shape fits (A/B measurements, parity tests).  Both produce the same dropout masks (same counter hash over (sequence, head, query, key)). */
+int hamt_attn_set_impl(int v);
+
 /* fused attention, head_dim 64: out = dropout(softmax(q k^T * scale + mask)) v ; vilmodel.py:96-129 (self), :322-349 (cross).
  * element (b,s,h,d) of q at q + b*q_bstride + s*ldq + h*64 + d (same for k/v with kv strides, out with o strides).
  * mask: additive fp32 [B,Sk] (the reference's (1-m)*-10000 row) or null.  lse: fp32 [B,heads,Sq] (needed for backward). */

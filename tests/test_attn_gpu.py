@@ -16,6 +16,18 @@ def _ops():
     return ops
 
 
+@pytest.fixture(params=["tcgen05", "legacy"])
+def impl(request):
+    """Every test runs twice: with the TMA + tcgen05 packed-tile kernels (default dispatch; shapes outside their envelope fall
+    through to the legacy kernels) and with the legacy mma.sync kernels forced (hamt_attn_set_impl(1))."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib
+    lib = _lib.load()
+    lib.hamt_attn_set_impl(1 if request.param == "legacy" else 2)
+    yield request.param
+    lib.hamt_attn_set_impl(0)
+
+
 def _ref(q, k, v, mask, B, Sq, Sk):
     qh = q.float().view(B, Sq, HEADS, D).permute(0, 2, 1, 3)
     kh = k.float().view(B, Sk, HEADS, D).permute(0, 2, 1, 3)
@@ -30,8 +42,12 @@ def _ref(q, k, v, mask, B, Sq, Sk):
 @pytest.mark.parametrize("B,Sq,Sk,masked", [(3, 36, 36, False), (4, 80, 80, True), (4, 80, 53, True), (4, 53, 80, True), (2, 16, 5, True),
                                              (2, 1, 17, True), (2, 128, 128, True), (5, 17, 100, True),
                                              # long sequences (RxR instructions, BASELINE config 4: L = 300, 58 vision tokens): recompute backward
-                                             (2, 300, 300, True), (2, 300, 58, True), (2, 58, 300, True), (1, 129, 40, False), (1, 250, 512, True)])
-def test_attention_fwd_bwd(B, Sq, Sk, masked):
+                                             (2, 300, 300, True), (2, 300, 58, True), (2, 58, 300, True), (1, 129, 40, False), (1, 250, 512, True),
+                                             # tile-packing regimes of the tcgen05 kernels: 4 / 3 (+ shared remainder warp) / 2 / 1 problems per
+                                             # 128-row tile, packed key axis cut to fit TMEM, several query tiles per problem
+                                             (6, 16, 16, True), (7, 16, 80, True), (3, 40, 40, True), (3, 33, 36, False), (2, 41, 41, True),
+                                             (2, 64, 24, True), (2, 78, 78, True), (2, 36, 80, True), (1, 32, 128, True), (5, 53, 53, True)])
+def test_attention_fwd_bwd(B, Sq, Sk, masked, impl):
     ops = _ops()
     g = torch.Generator().manual_seed(B * 1000 + Sq * 10 + Sk)
     self_attn = Sq == Sk
@@ -85,7 +101,7 @@ def test_attention_fwd_bwd(B, Sq, Sk, masked):
     assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
-def test_attention_fully_masked_rows_match_reference():
+def test_attention_fully_masked_rows_match_reference(impl):
     """-10000 masks (not -inf): a fully masked key row still yields the reference's softmax over the raw scores."""
     ops = _ops()
     B, S = 2, 20
@@ -97,7 +113,7 @@ def test_attention_fully_masked_rows_match_reference():
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-def test_attention_dropout_statistics_and_backward_consistency():
+def test_attention_dropout_statistics_and_backward_consistency(impl):
     """With V = identity-like probes the output exposes dropout(P); check keep-rate and that the backward
     (which regenerates the mask) matches autograd through the explicitly recovered mask."""
     ops = _ops()
@@ -129,3 +145,27 @@ def test_attention_dropout_statistics_and_backward_consistency():
     ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:, :768], dqkv[:, 768:1536], dqkv[:, 1536:], B, S, S, HEADS, None, drop)
     for got, want in ((dqkv[:, :768], qr.grad), (dqkv[:, 768:1536], kr.grad), (dqkv[:, 1536:], vr.grad)):
         assert (got.float() - want).abs().max().item() < 6e-2 * max(1.0, want.abs().max().item())
+
+
+def test_attention_implementations_agree_bitwise_on_the_dropout_mask():
+    """The tcgen05 and the legacy kernels draw the SAME dropout mask (one counter hash over (sequence, head, query, key)), so a forward
+    of one and a backward of the other stay consistent; outputs agree to bf16 rounding."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    B, S, p = 3, 36, 0.3
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(B * S, 2304, generator=g).to(torch.bfloat16).cuda()
+    q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    drop = ops.Drop(torch.tensor([4242], dtype=torch.int64, device="cuda"), 7, p)
+    outs = []
+    for mode in (2, 1):
+        lib.hamt_attn_set_impl(mode)
+        try:
+            outs.append(ops.attn_fwd(q, k, v, B, S, S, HEADS, None, drop))
+        finally:
+            lib.hamt_attn_set_impl(0)
+    (o0, l0), (o1, l1) = outs
+    assert (o0.float() - o1.float()).abs().max().item() < 2e-2
+    assert (l0 - l1).abs().max().item() < 1e-3

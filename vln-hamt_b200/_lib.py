@@ -42,6 +42,7 @@ SIGNATURES = {
     "hamt_gemm_set_auto_pair": [i32],
     "hamt_gemm_set_sm_limit": [i32],
     "hamt_gemm_set_wide_epilogue": [i32],
+    "hamt_attn_set_impl": [i32],
     "hamt_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
     "hamt_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, u32, f32, vp],
     "hamt_attn_fwd": [vp, vp, vp, ll, ll, ll, ll, vp, vp, ll, ll, vp, i32, i32, i32, i32, f32, vp, u32, f32, vp],

@@ -121,6 +121,7 @@ int hamt_mul_rows_bf16(const void* a, const void* v, void* out, int B, int S, in
 
 int hamt_gemm_set_sm_limit(int n) { gemm_set_sm_limit(n); return 0; }
 int hamt_gemm_set_wide_epilogue(int on) { gemm_set_wide_epilogue(on); return 0; }
+int hamt_attn_set_impl(int v) { attn_set_impl(v); return 0; }
 int hamt_adamw_workspace_floats(void) { return adamw_workspace_floats(); }
 int hamt_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, long long total, const int* chunk_seg, const long long* seg_end, int nseg,
                     const unsigned char* seg_active, const float* seg_wd, int* seg_step, float* seg_step_size, const float* lr, double beta1,

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const DropState ds = drop_init(p.drop);
+  const AttnDrop ds = attn_drop_init(p.drop);
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
 
   for (int qb = warp; qb < Sq_pad / 16; qb += nwarps) {
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const AttnP p) {
           if (ds.on) {
             const int key = kb * 64 + nt * 8 + 2 * t + (e & 1);
             const int row = row0 + 8 * (e >> 1);
-            pd *= drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + row) * p.Sk + key);
+            pd *= attn_drop_mult(ds, attn_drop_rowkey(ds, (unsigned long long)blockIdx.x * p.Sq + row), key);
           }
           s[nt][e] = pd;
         }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
-  const DropState ds = drop_init(p.drop);
+  const AttnDrop ds = attn_drop_init(p.drop);
   const uint32_t sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDS_a = smem_u32(sDS);
 
   for (int kw = warp; kw < Sk_pad / 16; kw += nwarps) {
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
           float pe = 0.f, mult = 1.f;
           if (key < p.Sk && qi < p.Sq) {
             pe = __expf(st[nt][e] * p.scale + sMask[key] - sLse[qi]);
-            if (ds.on) mult = drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + qi) * p.Sk + key);
+            if (ds.on) mult = attn_drop_mult(ds, attn_drop_rowkey(ds, (unsigned long long)blockIdx.x * p.Sq + qi), key);
           }
           pd[nt][e] = pe * mult;
           dsv[nt][e] = pe * (dpt[nt][e] * mult - sDelta[qi]) * p.scale;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP
             float pe = 0.f, mult = 1.f;
             if (key < p.Sk && qi < p.Sq) {
               pe = __expf(sc[nt][e] * p.scale + sMask[key] - lse_r[e >> 1]);
-              if (ds.on) mult = drop_mult(ds, ((unsigned long long)blockIdx.x * p.Sq + qi) * p.Sk + key);
+              if (ds.on) mult = attn_drop_mult(ds, attn_drop_rowkey(ds, (unsigned long long)blockIdx.x * p.Sq + qi), key);
             }
             dsv[nt][e] = pe * (dp_[nt][e] * mult - del_r[e >> 1]) * p.scale;
           }
@@ -476,6 +476,10 @@ static AttnP to_params(const AttnArgs& a) {
 
 int attn_fwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_common(a)) return rc;
+  {
+    int rc = 0;
+    if (attn_fwd_tc(a, st, &rc)) return rc;      // TMA + tcgen05 packed-tile kernel; shapes outside its envelope fall through
+  }
   AttnP p = to_params(a);
   const int Sq_pad = (a.Sq + 15) & ~15, Sk_pad = (a.Sk + 63) & ~63, Sk_rows = (a.Sk + 15) & ~15;
   const size_t smem = (size_t)(Sq_pad + 2 * Sk_rows) * LDS * 2 + Sk_pad * 4;

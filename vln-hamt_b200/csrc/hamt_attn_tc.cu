@@ -17,13 +17,13 @@
 // O = Pd V is ONE MMA over the packed key axis with a block-diagonal Pd: every softmax thread writes its whole row of Pd (bf16, K-major,
 // 128-byte swizzle) with zeros outside its own key window.
 //
-// Warp roles (320 threads, one persistent CTA per SM, static round-robin tile list):
+// Warp roles (384 threads, one persistent CTA per SM, static round-robin tile list):
 //   warp 0      TMA producer: Q / K / V boxes of the tile's problems straight out of the fused [tokens, 3H] projection buffer through
 //               3-D tensor maps (column, position, sequence) -- rows past the end of a sequence are zero-filled by the TMA unit, so the
 //               padding of the packed tile needs no extra pass -- into a ring of NS shared-memory stages;
 //   warp 1      TMEM owner and single-thread tcgen05.mma issuer: S = Q K^T as soon as a stage lands, O = Pd V as soon as the softmax
 //               warps publish Pd; order QK(i+1) before PV(i) so the tensor pipe never waits for the softmax of the same tile;
-//   warps 2-5 / 6-9   two softmax warpgroups working on alternate tiles (each has its own S / O TMEM columns and Pd buffer): tcgen05.ld of the
+//   warps 4-7 / 8-11  two softmax warpgroups working on alternate tiles (each has its own S / O TMEM columns and Pd buffer): tcgen05.ld of the
 //               lane's key window -> scale + additive mask (divide-then-add, -10000 masks as in the reference) -> max / exp2 / sum with
 //               one thread per row (no shuffles) -> dropout on the probabilities -> Pd to shared memory -> later the O tile: tcgen05.ld,
 //               1/l scaling, bf16, swizzled staging, ONE TMA store per warp (rows past the sequence end are clipped by the TMA unit).
@@ -37,8 +37,7 @@ namespace hamt {
 
 namespace tc {
 
-static constexpr int kThreads = 320;
-static constexpr int kLog2eNum = 0;  // (placeholder to keep the namespace non-empty for older compilers)
+static constexpr int kThreads = 384;     // warps 0..3: TMA producer, MMA issuer, 2 spare; warps 4..7 and 8..11: the two softmax warpgroups
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -83,24 +82,21 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
-// Columns [0, w) of a TMEM row window into v[0 .. NCH*32): full 32-column chunks, then a tail of 8 / 16 / 24 columns (w is a
-// multiple of 8, warp-uniform); registers past w are set to zero.  The caller issues tmem_ld_wait() before reading v.
-template <int NCH>
-__device__ __forceinline__ void load_window(uint32_t taddr, int w, uint32_t (&v)[NCH * 32]) {
+// Columns [0, NU * 8) of a TMEM row window into v: full 32-column chunks, then a tail of 8 / 16 / 24 columns.  The caller issues
+// tmem_ld_wait() before reading v.
+template <int NU>
+__device__ __forceinline__ void load_window(uint32_t taddr, uint32_t (&v)[NU * 8]) {
+  constexpr int W = NU * 8;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int rem = w - c * 32;
-    if (rem >= 32) {
-      tmem_ld_x32(taddr + c * 32, &v[c * 32]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[c * 32 + j] = 0u;
+  for (int c = 0; c * 32 < W; ++c) {
+    constexpr int dummy = 0; (void)dummy;
+    const int rem = W - c * 32;          // compile-time after unrolling
+    if (rem >= 32) tmem_ld_x32(taddr + c * 32, &v[c * 32]);
+    else {
       if (rem >= 16) {
         tmem_ld_x16(taddr + c * 32, &v[c * 32]);
         if (rem >= 24) tmem_ld_x8(taddr + c * 32 + 16, &v[c * 32 + 16]);
-      } else if (rem >= 8) {
-        tmem_ld_x8(taddr + c * 32, &v[c * 32]);
-      }
+      } else if (rem >= 8) tmem_ld_x8(taddr + c * 32, &v[c * 32]);
     }
   }
 }
@@ -122,7 +118,8 @@ struct FwdParams {
   int ns;                 // input stages
   int nwg;                // softmax warpgroups in use (2, or 1 when the score tile needs more than half of TMEM)
   uint32_t stage_bytes, off_k, off_v;     // per input stage: Q at 0, K at off_k, V at off_v
-  uint32_t off_p, p_bytes;                // Pd buffers (one per warpgroup), from the start of dynamic smem
+  uint32_t off_pd;                        // Pd inside the stage: on top of the Q / K tiles (dead after S = Q K^T)
+  uint32_t off_stg;                       // output staging (16 KB per warpgroup), from the start of dynamic smem
   uint32_t off_mask, mask_floats;         // per softmax warp: nwin * NCH*32 floats
   uint32_t off_bar;
   uint32_t tx_q32, tx_q8, tx_kv;          // bytes of one Q box (32 rows), one remainder box (8 rows), one K or V box
@@ -141,7 +138,7 @@ struct RowMap {
 };
 __device__ __forceinline__ RowMap row_map(const Geom& g, int slot, int lane, int qt) {
   RowMap r;
-  if (g.regime == 0) { r.pi = slot; r.qrow = lane; r.ok = lane < g.Sq; }
+  if (g.regime == 0) { r.pi = slot; r.qrow = lane; r.ok = lane < g.Sq && slot < g.P; }
   else if (g.regime == 1) {
     if (slot < 3) { r.pi = slot; r.qrow = lane; r.ok = true; }
     else { r.pi = lane >> 3; r.qrow = 32 + (lane & 7); r.ok = r.pi < 3 && r.qrow < g.Sq; }
@@ -153,7 +150,11 @@ __device__ __forceinline__ RowMap row_map(const Geom& g, int slot, int lane, int
 // ------------------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------------------
-template <int NCH>
+// NU = key-window width in groups of 8 keys (W = 8 NU); MULTI = the 3-problem layout whose fourth warp holds rows of all three problems.
+// Both are compile-time so that every instantiation carries only its own straight-line softmax: the first version (runtime widths,
+// both layouts in one kernel) was 4.5 k SASS instructions and lost 28 % of its issue slots to instruction fetch
+// (profiles/r02_ncu_attn_fwd_v1.txt).
+template <int NU, bool MULTI>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qr, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_or,
@@ -161,6 +162,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const Geom& g = p.g;
+  constexpr int NCH = (NU + 3) / 4;           // 32-column chunks of a key window (mask staging granularity)
+  constexpr int W = NU * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_base = smem_base + p.off_bar;
   // barriers: full[ns], empty[ns], s_full[2], p_full[2], o_full[2], o_empty[2], tmem ptr
@@ -181,10 +184,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr_addr);
-  // K / V stages start from zeros: rows of the packed key axis that no TMA box ever writes (alignment padding, absent problems of a
-  // partial last tile) must hold finite values -- they meet zero probabilities in the PV product
-  for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)p.ns * p.stage_bytes; i += kThreads * 16u)
-    *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  // Rows of the packed key axis that no TMA box ever writes (alignment padding behind the last problem; whole problem windows when
+  // the last tile is partial) must hold finite values: they meet zero probabilities in the PV product.
+  if (g.nprob % g.P != 0) {
+    for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)p.ns * p.stage_bytes; i += kThreads * 16u)
+      *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  } else {
+    const uint32_t r0 = (uint32_t)(g.P * W) * 128u, r1 = (uint32_t)g.n_total * 128u;       // byte range inside a V tile
+    for (int s = 0; s < p.ns; ++s)
+      for (uint32_t i = r0 + threadIdx.x * 16u; i < r1; i += kThreads * 16u)
+        *reinterpret_cast<uint4*>(smem_raw + (uint32_t)s * p.stage_bytes + p.off_v + i) = make_uint4(0, 0, 0, 0);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -243,55 +253,72 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
+      // Two kinds of work, issued in whatever order their inputs become ready (non-blocking mbarrier tests): S = Q K^T of the next
+      // tile as soon as its stage has landed, O = Pd V as soon as the softmax warps have published Pd.  (A fixed issue order makes
+      // PV(i) wait for the TMA of tile i + 1 and serialises the softmax warpgroups on memory latency.)
       const uint32_t idesc_s = umma_idesc_bf16(128, g.n_total, false, false);     // S = Q (K-major) x K^T (K-major)
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);             // O = Pd (K-major) x V (MN-major: d contiguous)
-      auto issue_pv = [&](int j) {
-        const int w = j % p.nwg, s = j % p.ns;
-        const uint32_t use = (uint32_t)(j / p.nwg);          // how many tiles this warpgroup has handled before
-        mbar_wait(pfull_bar(w), use & 1u);                   // Pd of tile j is in shared memory (and S of tile j has been read)
-        mbar_wait(oempty_bar(w), (use & 1u) ^ 1u);           // the O accumulator of this warpgroup's previous tile has been drained
-        tc_fence_after();
-        const uint32_t sv = smem_base + (uint32_t)s * p.stage_bytes + p.off_v;
-        const uint32_t sp = smem_base + p.off_p + (uint32_t)w * p.p_bytes;
-        const uint32_t d_tmem = tmem_base + o_col(w);
-        const int ksteps = g.n_total >> 4;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t da = umma_smem_desc(sp + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u, 16, 1024);
-          const uint64_t db = umma_smem_desc(sv + (uint32_t)k * 2048u, 8192, 1024);
-          umma_bf16(d_tmem, da, db, idesc_o, k > 0 ? 1u : 0u);
-        }
-        umma_commit(ofull_bar(w));
-        umma_commit(empty_bar(s));            // Q / K / V of this stage are no longer needed
-      };
-      for (int i = 0; i < n_my; ++i) {
-        const int w = i % p.nwg, s = i % p.ns;
-        mbar_wait(full_bar(s), (uint32_t)(i / p.ns) & 1u);
-        // S columns of warpgroup w are free: Pd of its previous tile was published (waited for in issue_pv(i - nwg)) after S was read
-        tc_fence_after();
-        const uint32_t sq = smem_base + (uint32_t)s * p.stage_bytes, sk = sq + p.off_k;
-        const uint32_t d_tmem = tmem_base + s_col(w);
+      int qk_i = 0, pv_j = 0;
+      unsigned long long t0 = 0;
+      uint32_t idle = 0;
+      while (pv_j < n_my) {
+        bool progressed = false;
+        // S columns of warpgroup w are free once Pd of its previous tile was published (observed before PV of that tile was issued)
+        if (qk_i < n_my && qk_i < pv_j + p.nwg) {
+          const int w = qk_i % p.nwg, st = qk_i % p.ns;
+          if (mbar_test_wait(full_bar(st), (uint32_t)(qk_i / p.ns) & 1u)) {
+            tc_fence_after();
+            const uint32_t sq = smem_base + (uint32_t)st * p.stage_bytes, sk = sq + p.off_k;
+            const uint32_t d_tmem = tmem_base + s_col(w);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = umma_smem_desc(sq + k * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(sk + k * 32, 16, 1024);
-          umma_bf16(d_tmem, da, db, idesc_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc(sq + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(sk + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc_s, k > 0 ? 1u : 0u);
+            }
+            umma_commit(sfull_bar(w));
+            ++qk_i;
+            progressed = true;
+          }
         }
-        umma_commit(sfull_bar(w));
-        if (i >= p.nwg - 1 && i - (p.nwg - 1) >= 0 && p.nwg == 2) { if (i >= 1) issue_pv(i - 1); }
-        else if (p.nwg == 1) issue_pv(i);
+        if (pv_j < qk_i) {
+          const int w = pv_j % p.nwg, st = pv_j % p.ns;
+          const uint32_t use = (uint32_t)(pv_j / p.nwg);       // tiles this warpgroup has handled before
+          // Pd of tile pv_j is in shared memory (and its S has been read); the O accumulator of the warpgroup's previous tile is drained
+          if (mbar_test_wait(pfull_bar(w), use & 1u) && mbar_test_wait(oempty_bar(w), (use & 1u) ^ 1u)) {
+            tc_fence_after();
+            const uint32_t sbase = smem_base + (uint32_t)st * p.stage_bytes;
+            const uint32_t sv = sbase + p.off_v, sp = sbase + p.off_pd;
+            const uint32_t d_tmem = tmem_base + o_col(w);
+            const int ksteps = g.n_total >> 4;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t da = umma_smem_desc(sp + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u, 16, 1024);
+              const uint64_t db = umma_smem_desc(sv + (uint32_t)k * 2048u, 8192, 1024);
+              umma_bf16(d_tmem, da, db, idesc_o, k > 0 ? 1u : 0u);
+            }
+            umma_commit(ofull_bar(w));
+            umma_commit(empty_bar(st));           // Q / K / V / Pd of this stage are no longer needed
+            ++pv_j;
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if ((++idle & 0xfffu) == 0) {        // bounded: a protocol bug traps instead of hanging the GPU
+          if (t0 == 0) t0 = globaltimer_ns();
+          else if (globaltimer_ns() - t0 > 4000000000ull) { printf("hamt attn: MMA issuer stalled (block %d qk %d pv %d of %d)\n", blockIdx.x, qk_i, pv_j, n_my); __trap(); }
+        }
       }
-      if (p.nwg == 2 && n_my > 0) issue_pv(n_my - 1);
     }
-  } else {
+  } else if (warp >= 4) {
     // ===================== softmax + output warps =====================
-    const int wg = (warp - 2) >> 2;              // warpgroup 0: warps 2..5, warpgroup 1: warps 6..9
+    const int wg = (warp - 4) >> 2;              // warpgroup 0: warps 4..7, warpgroup 1: warps 8..11
     const int slot = warp & 3;                   // TMEM lane quarter this warp may access = 32-row slot of the tile
     if (wg < p.nwg) {
-      const DropState ds = drop_init(p.drop);
-      const bool multi = g.regime == 1 && slot == 3;
-      float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)((warp - 2) * p.mask_floats);
-      uint8_t* pbuf = smem_raw + p.off_p + (uint32_t)wg * p.p_bytes;
-      const uint32_t pbuf_a = smem_base + p.off_p + (uint32_t)wg * p.p_bytes;
+      const AttnDrop ds = attn_drop_init(p.drop);
+      const bool multi = MULTI && slot == 3;
+      float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)((warp - 4) * p.mask_floats);
+      uint8_t* stg = smem_raw + p.off_stg + (uint32_t)wg * 16384u;       // this warpgroup's output staging tile
+      const uint32_t stg_a = smem_base + p.off_stg + (uint32_t)wg * 16384u;
       const int row = slot * 32 + lane;          // row of the tile = TMEM lane
       const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
       int use = 0;
@@ -304,7 +331,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const bool valid = rm.ok && pr < g.nprob;
         const int b = valid ? pr / heads : 0, h = valid ? pr % heads : 0;
         // ---- additive mask rows of the key window(s) this warp looks at, in log2 units; padded keys carry -inf
-        {
+        if (p.mask_floats != 0) {
           const int nw = multi ? g.nwin : 1;
           for (int wdx = 0; wdx < nw; ++wdx) {
             const int prw = multi ? p0 + wdx : __shfl_sync(0xffffffffu, pr, 0);
@@ -316,74 +343,93 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               smask[wdx * NCH * 32 + j] = mv;
             }
           }
-          // the previous tile's output store must have finished READING the staging rows (they alias this warp's Pd rows)
-          if (lane == 0) tma_store_wait_read();
           __syncwarp();
         }
         mbar_wait(sfull_bar(wg), (uint32_t)use & 1u);
         tc_fence_after();
         // ---- scores of this lane's key window
-        uint32_t sv[NCH * 32];
+        uint32_t sv[NU * 8];
         const uint32_t t_s = tmem_base + lane_field + s_col(wg);
-        if (!multi) {
-          load_window<NCH>(t_s + (uint32_t)(__shfl_sync(0xffffffffu, rm.pi, 0) * g.W), g.W, sv);
+        if (!MULTI || !multi) {
+          // (warps whose slot holds no problem still take part in the warp-collective load: window 0)
+          const int wpi = __shfl_sync(0xffffffffu, valid ? rm.pi : 0, 0);
+          load_window<NU>(t_s + (uint32_t)(wpi * W), sv);
           tmem_ld_wait();
-        } else {
-          // remainder warp: its lanes belong to different problems -> fetch every window chunk-wise and keep the lane's own
+        } else if constexpr (MULTI) {
+          // remainder warp: its lanes belong to different problems -> fetch the three windows 16 columns at a time and keep the lane's own
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t t0[32], t1[32], t2[32];
-            const int rem = g.W - c * 32;
-            if (rem > 0) {
-              // (windows are read with full 32-column loads here: columns past a window are the next window / padding, never used)
-              tmem_ld_x32(t_s + 0 * g.W + c * 32, t0);
-              tmem_ld_x32(t_s + 1 * g.W + c * 32, t1);
-              tmem_ld_x32(t_s + 2 * g.W + c * 32, t2);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sv[c * 32 + j] = (c * 32 + j < g.W) ? (rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j])) : 0u;
+          for (int c = 0; c < NU * 8; c += 16) {
+            uint32_t t0[16], t1[16], t2[16];
+            if (c + 16 <= NU * 8) {
+              tmem_ld_x16(t_s + 0 * W + c, t0); tmem_ld_x16(t_s + 1 * W + c, t1); tmem_ld_x16(t_s + 2 * W + c, t2);
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sv[c * 32 + j] = 0u;
+              tmem_ld_x8(t_s + 0 * W + c, t0); tmem_ld_x8(t_s + 1 * W + c, t1); tmem_ld_x8(t_s + 2 * W + c, t2);
             }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j < NU * 8) sv[c + j] = rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j]);
           }
         }
-        const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
         float mx = -INFINITY;
+        if (p.mask_floats != 0) {
+          const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
 #pragma unroll
-        for (int j = 0; j < NCH * 32; ++j) {
-          const float t = fmaf(__uint_as_float(sv[j]), p.scale_log2, mrow[j]);      // padded keys: 0 * c + (-inf)
-          sv[j] = __float_as_uint(t);
-          mx = fmaxf(mx, t);
+          for (int kk = 0; kk < NU; ++kk) {
+            const float4 m0 = *reinterpret_cast<const float4*>(mrow + kk * 8), m1 = *reinterpret_cast<const float4*>(mrow + kk * 8 + 4);
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = fmaf(__uint_as_float(sv[kk * 8 + e]), p.scale_log2, mm[e]);      // padded keys: 0 * c + (-inf)
+              sv[kk * 8 + e] = __float_as_uint(t);
+              mx = fmaxf(mx, t);
+            }
+          }
+        } else {        // no mask (the panorama encoder attends to all 36 views): only the padded keys of the last group are excluded
+#pragma unroll
+          for (int j = 0; j < NU * 8; ++j) {
+            float t = __uint_as_float(sv[j]) * p.scale_log2;
+            if (j >= (NU - 1) * 8 && j >= g.Sk) t = -INFINITY;
+            sv[j] = __float_as_uint(t);
+            mx = fmaxf(mx, t);
+          }
         }
-        float l = 0.f;
-        const unsigned long long rbase = ((unsigned long long)pr * g.Sq + rm.qrow) * g.Sk;
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NCH * 32; ++j) {
-          const float pe = ex2_approx(__uint_as_float(sv[j]) - mx);
-          l += pe;
-          float pd = pe;
-          if (ds.on) pd *= drop_mult(ds, rbase + j);
-          sv[j] = __float_as_uint(pd);
+        for (int j = 0; j < NU * 8; j += 2) {
+          const float pa = ex2_approx(__uint_as_float(sv[j]) - mx), pb = ex2_approx(__uint_as_float(sv[j + 1]) - mx);
+          l0 += pa; l1 += pb;
+          sv[j] = __float_as_uint(pa); sv[j + 1] = __float_as_uint(pb);
+        }
+        const float l = l0 + l1;
+        if (ds.on) {          // dropout on the probabilities: one hash per pair of keys
+          const uint32_t rowkey = attn_drop_rowkey(ds, (unsigned long long)pr * g.Sq + rm.qrow);
+#pragma unroll
+          for (int j = 0; j < NU * 8; j += 2) {
+            const uint32_t bits = attn_drop_bits(rowkey, (uint32_t)(j >> 1));
+            const float ma = (bits & 0xffffu) < ds.thresh16 ? 0.f : ds.scale, mb = (bits >> 16) < ds.thresh16 ? 0.f : ds.scale;
+            sv[j] = __float_as_uint(__uint_as_float(sv[j]) * ma);
+            sv[j + 1] = __float_as_uint(__uint_as_float(sv[j + 1]) * mb);
+          }
         }
         // ---- this lane's row of Pd: zeros outside its key window (16-byte units of 8 keys; unit u of row r lives at chunk u>>3,
-        //      byte r*128 + ((u&7) ^ (r&7))*16: the 128-byte swizzle the UMMA descriptor expects)
+        //      byte r*128 + ((u&7) ^ (r&7))*16: the 128-byte swizzle the UMMA descriptor expects).  Pd sits on top of the stage's
+        //      Q / K tiles: Q K^T has completed (s_full), nobody reads them any more.
         {
-          const int u0 = valid ? (rm.pi * g.W) >> 3 : 0x7fffffff, nu = g.W >> 3, units = kch * 8;
-          for (int u = 0; u < units; ++u) {
-            uint4 val = make_uint4(0, 0, 0, 0);
-            const int k = u - u0;
-            if (k >= 0 && k < nu) {
-              // static register indexing: the unit of the window is selected with an unrolled compare chain
+          uint8_t* prow = smem_raw + (uint32_t)(i % p.ns) * p.stage_bytes + p.off_pd + (uint32_t)row * 128u;
+          const uint32_t rx = (uint32_t)(row & 7);
+          const int units = kch * 8;
+          const int u0 = valid ? rm.pi * NU : units;        // rows that belong to no problem: all zeros
+          auto unit_ptr = [&](int u) { return reinterpret_cast<uint4*>(prow + (uint32_t)(u >> 3) * 16384u + ((((uint32_t)u & 7u) ^ rx) << 4)); };
+          for (int u = 0; u < u0; ++u) *unit_ptr(u) = make_uint4(0, 0, 0, 0);
+          for (int u = u0 + NU; u < units; ++u) *unit_ptr(u) = make_uint4(0, 0, 0, 0);
+          if (valid) {
 #pragma unroll
-              for (int kk = 0; kk < NCH * 4; ++kk)
-                if (kk == k)
-                  val = make_uint4(pack_bf16(__uint_as_float(sv[kk * 8 + 0]), __uint_as_float(sv[kk * 8 + 1])),
-                                   pack_bf16(__uint_as_float(sv[kk * 8 + 2]), __uint_as_float(sv[kk * 8 + 3])),
-                                   pack_bf16(__uint_as_float(sv[kk * 8 + 4]), __uint_as_float(sv[kk * 8 + 5])),
-                                   pack_bf16(__uint_as_float(sv[kk * 8 + 6]), __uint_as_float(sv[kk * 8 + 7])));
-            }
-            *reinterpret_cast<uint4*>(pbuf + (uint32_t)(u >> 3) * 16384u + (uint32_t)row * 128u + (uint32_t)(((u & 7) ^ (row & 7)) << 4)) = val;
+            for (int kk = 0; kk < NU; ++kk)
+                *unit_ptr(u0 + kk) = make_uint4(pack_bf16(__uint_as_float(sv[kk * 8 + 0]), __uint_as_float(sv[kk * 8 + 1])),
+                                                pack_bf16(__uint_as_float(sv[kk * 8 + 2]), __uint_as_float(sv[kk * 8 + 3])),
+                                                pack_bf16(__uint_as_float(sv[kk * 8 + 4]), __uint_as_float(sv[kk * 8 + 5])),
+                                                pack_bf16(__uint_as_float(sv[kk * 8 + 6]), __uint_as_float(sv[kk * 8 + 7])));
           }
         }
         fence_proxy_async();
@@ -403,7 +449,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(oempty_bar(wg));
         const float inv = 1.0f / l;
-        uint8_t* srow = pbuf + (uint32_t)row * 128u;          // staging = chunk 0 of this warpgroup's Pd buffer (PV has completed)
+        // the previous tile's output store must have finished READING this warp's staging rows
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        uint8_t* srow = stg + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t* src = c < 4 ? &o0[c * 8] : &o1[(c - 4) * 8];
@@ -414,11 +463,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          const uint32_t sst = pbuf_a + (uint32_t)(slot * 32) * 128u;
+          const uint32_t sst = stg_a + (uint32_t)(slot * 32) * 128u;
           if (!multi) {
-            const int pr0 = p0 + rm.pi;        // lane 0's problem = the warp's problem
-            const int q0 = rm.qrow;            // first query row of this warp's slot
-            if (pr0 < g.nprob && q0 < g.Sq) tma_store_3d(&tm_o, sst, (pr0 % heads) * 64, q0, pr0 / heads);
+            // lane 0 holds the first row of the warp's slot: if it maps to no problem row, neither does any other lane
+            if (valid) tma_store_3d(&tm_o, sst, (pr % heads) * 64, rm.qrow, pr / heads);
           } else {
             for (int wdx = 0; wdx < 3; ++wdx)
               if (p0 + wdx < g.nprob) tma_store_3d(&tm_or, sst + (uint32_t)wdx * 1024u, ((p0 + wdx) % heads) * 64, 32, (p0 + wdx) / heads);
@@ -479,7 +527,7 @@ static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal) {
   g.W = (Sk + 7) & ~7;
   if (g.W > 128) return false;                 // longer key axes: legacy kernel (RxR instructions)
   if (Sq <= 32) { g.regime = 0; g.P = 4; }
-  else if (Sq <= 40) { g.regime = 1; g.P = 3; }
+  else if (Sq <= 40 && g.W <= 64) { g.regime = 1; g.P = 3; }      // (the remainder warp holds three windows: compiled for W <= 64)
   else if (Sq <= 64) { g.regime = 2; g.P = 2; }
   else { g.regime = 3; g.P = 1; }
   // the packed key axis must fit the score tile; fall back to fewer problems per tile (regime 2 / 3 layouts)
@@ -497,7 +545,7 @@ static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal) {
   return true;
 }
 
-static int g_attn_impl = 0;        // hamt_attn_set_impl: 0 = auto (tcgen05 kernels where the shape fits), 1 = legacy mma.sync kernels only
+static int g_attn_impl = 0;        // hamt_attn_set_impl: 0 = auto (tcgen05 kernels where they win), 1 = legacy mma.sync kernels only, 2 = tcgen05 wherever the shape fits
 
 static int num_sms_cached() {
   static int n = 0;
@@ -510,24 +558,32 @@ static int num_sms_cached() {
   return n;
 }
 
-template <int NCH>
+template <int NU, bool MULTI>
 static int launch_fwd(const AttnArgs& a, const Geom& g, cudaStream_t st) {
+  constexpr int NCH = (NU + 3) / 4;
   FwdParams p{};
   p.g = g;
   p.nwg = 2;
   const uint32_t krows = (uint32_t)g.n_total;                       // rows of the packed K / V tiles
+  const uint32_t kch = (uint32_t)(g.n_total + 63) / 64;             // 64-key chunks of Pd, 16 KB each
+  const uint32_t pd_bytes = kch * 16384u;
   p.off_k = 16384u;
-  p.off_v = p.off_k + krows * 128u;
+  // Pd (kch chunks of 16 KB) lies on top of Q | K: both are dead once S = Q K^T has completed.  The K region is widened to whole
+  // chunks where necessary (at most 12 KB of slack) so that Pd never reaches V.
+  uint32_t k_bytes = krows * 128u;
+  if (k_bytes < (kch - 1) * 16384u) k_bytes = (kch - 1) * 16384u;
+  p.off_v = p.off_k + k_bytes;
+  p.off_pd = 0u;
   p.stage_bytes = p.off_v + krows * 128u;
-  p.p_bytes = (uint32_t)((g.n_total + 63) / 64) * 16384u;
-  p.mask_floats = (uint32_t)(g.nwin * NCH * 32);
-  const uint32_t fixed = 2 * p.p_bytes + 8u * p.mask_floats * 4u + 256u;
+  (void)pd_bytes;
+  p.mask_floats = a.mask != nullptr ? (uint32_t)(g.nwin * NCH * 32) : 0u;      // no staging without a mask
+  const uint32_t fixed = 2 * 16384u + 8u * p.mask_floats * 4u + 256u;
   int ns = (int)((232448u - 1024u - fixed) / p.stage_bytes);
-  if (ns > 4) ns = 4;
+  if (ns > 6) ns = 6;
   HAMT_REQUIRE(ns >= 2, "attn_fwd (tcgen05): shape does not fit two input stages");
   p.ns = ns;
-  p.off_p = (uint32_t)ns * p.stage_bytes;
-  p.off_mask = p.off_p + 2 * p.p_bytes;
+  p.off_stg = (uint32_t)ns * p.stage_bytes;
+  p.off_mask = p.off_stg + 2 * 16384u;
   p.off_bar = (p.off_mask + 8u * p.mask_floats * 4u + 15u) & ~15u;
   const size_t smem = p.off_bar + 256;
   p.tx_q32 = 32 * 128; p.tx_q8 = 8 * 128; p.tx_kv = (uint32_t)g.W * 128u; p.kv_box_rows = g.W;
@@ -542,7 +598,7 @@ static int launch_fwd(const AttnArgs& a, const Geom& g, cudaStream_t st) {
   if ((rc = make_map3(&tv, a.v, a.B, a.Sk, a.heads, a.ldkv, a.kv_bstride, g.W))) return rc;
   if ((rc = make_map3(&to, a.out, a.B, a.Sq, a.heads, a.ldo, a.o_bstride, 32))) return rc;
   if ((rc = make_map3(&tor, a.out, a.B, a.Sq, a.heads, a.ldo, a.o_bstride, 8))) return rc;
-  auto kern = attn_fwd_tc_kernel<NCH>;
+  auto kern = attn_fwd_tc_kernel<NU, MULTI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -563,11 +619,28 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t st, int* rc) {
   if (tc::g_attn_impl == 1) return 0;
   tc::Geom g;
   if (!tc::plan(g, a.B, a.heads, a.Sq, a.Sk, 192)) return 0;
-  const int nch = (g.W + 31) / 32;
-  if (nch == 1) *rc = tc::launch_fwd<1>(a, g, st);
-  else if (nch == 2) *rc = tc::launch_fwd<2>(a, g, st);
-  else if (nch == 3) *rc = tc::launch_fwd<3>(a, g, st);
-  else *rc = tc::launch_fwd<4>(a, g, st);
+  // Measured (profiles/r02_kbench_attn_fwd_v3.txt): with <= 32 query rows per problem (history-only vision stream of MLM / MRC / ITM:
+  // 16 x 80, 16 x 16) the whole launch is a handful of tiles per SM and the fixed pipeline latency of this kernel (TMA -> MMA -> softmax
+  // -> MMA -> TMA store) loses against the legacy kernel's 6 resident CTAs per SM (12.9 vs 9.1 us, 7.5 vs 4.6 us): those stay legacy
+  // unless the tcgen05 path is forced (hamt_attn_set_impl(2)).
+  if (g.regime == 0 && tc::g_attn_impl != 2) return 0;
+  const int nu = g.W / 8;
+  if (g.regime == 1) {
+    switch (nu) {
+#define HAMT_CASE(N_) case N_: *rc = tc::launch_fwd<N_, true>(a, g, st); break;
+      HAMT_CASE(1) HAMT_CASE(2) HAMT_CASE(3) HAMT_CASE(4) HAMT_CASE(5) HAMT_CASE(6) HAMT_CASE(7) HAMT_CASE(8)
+#undef HAMT_CASE
+      default: return 0;
+    }
+  } else {
+    switch (nu) {
+#define HAMT_CASE(N_) case N_: *rc = tc::launch_fwd<N_, false>(a, g, st); break;
+      HAMT_CASE(1) HAMT_CASE(2) HAMT_CASE(3) HAMT_CASE(4) HAMT_CASE(5) HAMT_CASE(6) HAMT_CASE(7) HAMT_CASE(8)
+      HAMT_CASE(9) HAMT_CASE(10) HAMT_CASE(11) HAMT_CASE(12) HAMT_CASE(13) HAMT_CASE(14) HAMT_CASE(15) HAMT_CASE(16)
+#undef HAMT_CASE
+      default: return 0;
+    }
+  }
   return 1;
 }
 

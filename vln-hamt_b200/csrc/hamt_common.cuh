@@ -141,6 +141,42 @@ __device__ __forceinline__ float drop_mult(const DropState& s, unsigned long lon
   return h < s.thresh ? 0.f : s.scale;
 }
 
+// Dropout on attention probabilities: one hash per PAIR of adjacent keys of a row, 16 bits each (drop when the 16-bit lane is below
+// p * 65536: p = 0.1 -> 0.100006).  The per-element hash above costs ~14 integer instructions -- more than the rest of the softmax
+// arithmetic of an element -- and the probabilities are the most numerous dropout site of the model (12 heads x S^2 per sequence).
+// All four attention kernels (tcgen05 and legacy, forward and backward) use this function, so any forward / backward combination
+// regenerates the same mask.  row_id = (sequence * heads + head) * Sq + query.
+struct AttnDrop {
+  uint32_t k0, k1, thresh16;
+  float scale;
+  bool on;
+};
+__device__ __forceinline__ AttnDrop attn_drop_init(const DropCfg& c) {
+  AttnDrop s;
+  s.on = c.p > 0.f;
+  s.k0 = s.k1 = 0; s.thresh16 = 0; s.scale = 1.f;
+  if (s.on) {
+    unsigned long long seed = *c.seed_ptr;
+    s.k0 = mix32((uint32_t)seed ^ (c.site * 0x9E3779B1u));
+    s.k1 = mix32((uint32_t)(seed >> 32) + c.site * 0x85EBCA77u + 0x165667B1u);
+    s.thresh16 = (uint32_t)fminf(c.p * 65536.0f + 0.5f, 65535.0f);
+    s.scale = 1.0f / (1.0f - c.p);
+  }
+  return s;
+}
+__device__ __forceinline__ uint32_t attn_drop_rowkey(const AttnDrop& s, unsigned long long row_id) {
+  return mix32(((uint32_t)row_id ^ s.k0) * 0x9E3779B1u + (uint32_t)(row_id >> 32) * 0xC2B2AE3Du + s.k1);
+}
+// 2 x 16 random bits for keys (2 * pair, 2 * pair + 1) of the row
+__device__ __forceinline__ uint32_t attn_drop_bits(uint32_t rowkey, uint32_t pair) { return mix32(rowkey + pair * 0x9E3779B1u); }
+// multiplier (0 or 1/(1-p)) of key `key` of the row
+__device__ __forceinline__ float attn_drop_mult(const AttnDrop& s, uint32_t rowkey, int key) {
+  if (!s.on) return 1.f;
+  const uint32_t b = attn_drop_bits(rowkey, (uint32_t)key >> 1);
+  const uint32_t lane16 = (key & 1) ? (b >> 16) : (b & 0xffffu);
+  return lane16 < s.thresh16 ? 0.f : s.scale;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory addressing, mbarrier, TMA
 // ---------------------------------------------------------------------------------------------
@@ -168,14 +204,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined time; a thread that polls several barriers uses this)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.  The timeout path is a separate function so that the
+// dozens of wait sites of a kernel do not each carry a timer loop and a printf call (instruction-cache footprint).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   unsigned long long t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -184,6 +232,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

@@ -53,6 +53,9 @@ struct AttnBwdArgs {
   float* dbq; float* dbk; float* dbv;                // fp32 [heads*64] or null: += column sums of dq / dk / dv (fused bias gradients)
 };
 int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+// tcgen05 / TMA kernels (hamt_attn_tc.cu): return 1 when they took the problem (status in *rc), 0 -> run the legacy kernel
+int attn_fwd_tc(const AttnArgs& a, cudaStream_t st, int* rc);
+void attn_set_impl(int v);      // 0 = auto, 1 = legacy mma.sync kernels only
 
 // text embedding: out = drop(LN(word[ids] + pos[s] + type0))
 int embed_text_fwd(const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma, const float* beta,
