@@ -32,6 +32,32 @@ SHAPE = dict(txt_len=80, hist_len=15, n_pano=36, n_ob=37, feat=768)
 # algorithmic forward GFLOP per sample; fwd+bwd = 3x
 FWD_GFLOP = dict(mlm=34.37, sap=36.78, sar=36.74, sprel=36.82, mrc=33.80, itm=63.25)
 
+# BASELINE.json configs: [1] = r2r (the headline, default), [3] = rxr (L = 300, 512-d features, XLM-R vocabulary 250 002, hist 20 x 36,
+# no MRC: pretrain_rxr.json), [4] = r4r (hist 40 x 36).  The other two are separate bench lines (--config), not the headline.
+CONFIGS = {
+    "r2r": dict(workload="R2R 6-task pretrain (cmt-vitbase-6tasks), txt80/hist15x36/obs37, schedule 5mlm:1sap:1sar:1sprel:2mrc:2itm",
+                shape=SHAPE, schedule=SCHEDULE, cfg={}, batch=64, ref_config="r2r_model_config.json"),
+    "rxr": dict(workload="RxR long-instruction stress (rxr_xlm_model_config: 512-d features, vocab 250002), txt300/hist20x36/obs37, schedule 5mlm:1sap:1sar:1sprel:2itm",
+                shape=dict(txt_len=300, hist_len=20, n_pano=36, n_ob=37, feat=512, vocab_hi=250000),
+                schedule=["mlm", "sap", "mlm", "itm", "mlm", "sar", "mlm", "sprel", "mlm", "itm"],
+                cfg=dict(image_feat_size=512, vocab_size=250002, max_position_embeddings=514), batch=64, ref_config="rxr_xlm_model_config.json"),
+    "r4r": dict(workload="R4R long-horizon history stress, txt80/hist40x36/obs37, schedule 5mlm:1sap:1sar:1sprel:2mrc:2itm",
+                shape=dict(txt_len=80, hist_len=40, n_pano=36, n_ob=37, feat=768), schedule=SCHEDULE, cfg={}, batch=64, ref_config="r2r_model_config.json"),
+}
+
+
+def fwd_gflop_per_sample(task, L, T, O=37, P=36, H=768, I=3072, layers_l=9, layers_x=4, layers_p=2):
+    """Algorithmic forward FLOPs of one sample (SURVEY 8a formulae: BertLayer = S(8H^2 + 4HI) + 4 S^2 H; x-layer =
+    (L + V)(16H^2 + 4HI) + 8 L V H + 4 L^2 H + 4 V^2 H); used for the non-headline configs (the headline uses SURVEY's table)."""
+    def bert(S):
+        return S * (8 * H * H + 4 * H * I) + 4 * S * S * H
+    has_ob = task in ("sap", "sar", "sprel")
+    V = T + 1 + (O if has_ob else 0)
+    R = 5 if task == "itm" else 1
+    f = layers_l * bert(L) + T * (layers_p * bert(P) + P * 2 * H * 768) + (T + (O if has_ob else 0)) * 2 * H * 768
+    f += R * layers_x * ((L + V) * (16 * H * H + 4 * H * I) + 8 * L * V * H + 4 * L * L * H + 4 * V * V * H)
+    return f / 1e9
+
 
 def batch_size_of(task, B):
     return B // 2 if task == "itm" else B
@@ -80,95 +106,107 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_samples_per_sec(steps, warmup, batch, threads=None, tasks=None):
-    """Times the oracle port (oracle/hamt_oracle.py, fp32, autograd fwd+bwd, train-mode dropout masks omitted) on the host."""
-    from oracle import hamt_oracle as O
+def reference_kind():
+    """'reference' when the unmodified reference sources are reachable (baseline/_ref installed by build(), or /root/reference),
+    else 'port' (oracle/hamt_oracle.py)."""
+    from oracle import ref_shim
+    return "reference" if ref_shim.reference_available() else "port"
+
+
+def reference_samples_per_sec(device, steps, warmup, conf, autocast=False, threads=None, tasks=None):
+    """fwd + bwd samples/s of the reference's own implementation of the path: the UNMODIFIED `MultiStepNavCMTPreTraining`
+    (pretrain_src/model/pretrain_cmt.py, imported through oracle/ref_shim.py) in train mode -- dropout ON (pretrain_r2r.json:21) --
+    at the bench's batch size and task schedule, on the host cores (device cpu, all threads) or as torch eager on one GPU
+    (fp32, or under torch.autocast(bfloat16)).  Falls back to the oracle port when the reference sources are absent."""
     import hamt_b200  # noqa: F401
     from hamt_b200 import synth
     from hamt_b200.config import HamtConfig
     from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    cfg = HamtConfig()
-    model = MultiStepNavCMTPreTraining(cfg)
-    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in synth.seeded_state_dict(model, seed=0).items()}
-    sd["mlm_head.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
-    del model
-    tasks = tasks or SCHEDULE
-    batches = [synth.make_batch(t, batch_size=batch_size_of(t, batch), seed=i, **SHAPE) for i, t in enumerate(tasks)]
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        threads = threads or os.cpu_count()
+        torch.set_num_threads(threads)
+    kind = reference_kind()
+    tasks = tasks or conf["schedule"]
+    B = conf["batch"]
+    batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_batch(t, batch_size=batch_size_of(t, B), seed=i, **conf["shape"]).items()}
+               for i, t in enumerate(tasks)]
+    if kind == "reference":
+        from oracle import ref_shim
+        cfg = ref_shim.pretrain_config(config_name=conf["ref_config"])
+        model = ref_shim.load_pretrain_model(cfg)
+        model.load_state_dict(synth.seeded_state_dict(model, seed=0, perturb_ln=False))
+        model = model.to(dev).train()
+
+        def fwd_bwd(i, t):
+            loss = model(batches[i], t, compute_loss=True)
+            loss.float().mean().backward()
+            model.zero_grad(set_to_none=True)
+    else:
+        from oracle import hamt_oracle as O
+        cfg = HamtConfig(**conf["cfg"])
+        m = MultiStepNavCMTPreTraining(cfg)
+        sd = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in synth.seeded_state_dict(m, seed=0).items()}
+        sd["mlm_head.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
+        del m
+
+        def fwd_bwd(i, t):
+            loss = O.pretrain_forward(sd, cfg, batches[i], t, compute_loss=True)
+            loss.float().mean().backward()
+            for v in sd.values():
+                v.grad = None
+    gpu = dev.type == "cuda"
+    if gpu:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n, t0 = 0, None
     for i in range(warmup + steps):
         if i == warmup:
-            t0, n = time.perf_counter(), 0
-        t = tasks[i % len(tasks)]
+            n = 0
+            if gpu:
+                torch.cuda.synchronize(); e0.record()
+            t0 = time.perf_counter()
+        j = i % len(tasks)
         np.random.seed(i); torch.manual_seed(i)
-        loss = O.pretrain_forward(sd, cfg, batches[i % len(tasks)], t, compute_loss=True)
-        loss.mean().backward()
-        for v in sd.values():
-            v.grad = None
-        n += batch_size_of(t, batch)
-    dt = time.perf_counter() - t0
-    return n / dt, dt, threads
-
-
-def gpu_eager_port_samples_per_sec(batch=64, steps=12, warmup=12, autocast=True):
-    """Informational third column of SURVEY 8(d): the same oracle port run as plain torch eager ON THE GPU (train mode without
-    dropout masks, fwd + bwd, CUDA events) -- what 'reference GPU torch eager, 1 x B200' costs on this box.  The unmodified reference
-    cannot travel to the GPU box (it lives outside the repo), the port issues the same aten ops per layer."""
-    from oracle import hamt_oracle as O
-    import hamt_b200  # noqa: F401
-    from hamt_b200 import synth
-    from hamt_b200.config import HamtConfig
-    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
-    dev = torch.device("cuda", 0)
-    cfg = HamtConfig()
-    model = MultiStepNavCMTPreTraining(cfg)
-    sd = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in synth.seeded_state_dict(model, seed=0).items()}
-    sd["mlm_head.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
-    del model
-    batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synth.make_batch(t, batch_size=batch_size_of(t, batch), seed=i, **SHAPE).items()}
-               for i, t in enumerate(SCHEDULE)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 0
-    for i in range(warmup + steps):
-        if i == warmup:
-            torch.cuda.synchronize(); e0.record(); n = 0
-        t = SCHEDULE[i % len(SCHEDULE)]
-        np.random.seed(i); torch.manual_seed(i)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            loss = O.pretrain_forward(sd, cfg, batches[i % len(SCHEDULE)], t, compute_loss=True)
-        loss.float().mean().backward()
-        for v in sd.values():
-            v.grad = None
-        n += batch_size_of(t, batch)
-    e1.record(); torch.cuda.synchronize()
-    return n / (e0.elapsed_time(e1) * 1e-3)
+        with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+            fwd_bwd(j, tasks[j])
+        n += batch_size_of(tasks[j], B)
+    if gpu:
+        e1.record(); torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3
+    else:
+        dt = time.perf_counter() - t0
+    return n / dt, dt, (threads if dev.type == "cpu" else None), kind
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    batch = args.ref_batch
-    sps, dt, threads = cpu_reference_samples_per_sec(args.steps, args.warmup, batch)
+    conf = CONFIGS[args.config]
+    warm = min(args.warmup, 2)       # CPU steps take seconds each: two untimed steps settle the allocator / thread pool
+    sps, dt, threads, kind = reference_samples_per_sec("cpu", args.steps, warm, conf)
+    B = conf["batch"]
+    what = ("unmodified reference MultiStepNavCMTPreTraining (baseline/_ref via oracle/ref_shim.py)" if kind == "reference"
+            else "oracle port (oracle/hamt_oracle.py; reference sources not found)")
     gpu_eager = None
     if torch.cuda.is_available() and not args.no_gpu_eager:
-        gpu_eager = {"what": "oracle port as torch eager on 1 GPU, batch 64, 6-task schedule, fwd+bwd, CUDA events (informational; not the reference arm's value)"}
+        gpu_eager = {"what": f"{what} as torch eager on 1 GPU, train mode (dropout on), batch {B}, same schedule, fwd+bwd, CUDA events, 12 steps after 6 "
+                             "(informational; not the reference arm's value)"}
         for name, ac in (("bf16_autocast", True), ("fp32", False)):
             try:
-                gpu_eager[name + "_samples_per_s"] = round(gpu_eager_port_samples_per_sec(autocast=ac), 1)
+                gpu_eager[name + "_samples_per_s"] = round(reference_samples_per_sec("cuda:0", 12, 6, conf, autocast=ac)[0], 1)
             except Exception as e:  # noqa: BLE001
                 gpu_eager[name + "_error"] = f"{type(e).__name__}: {str(e)[:200]}"
             torch.cuda.empty_cache()
     line = {"impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "R2R 6-task pretrain, txt80/hist15x36/obs37, 5:1:1:1:2:2 schedule", "global_batch": batch,
-                       "note": f"bounded sample: per-step batch {batch} (ITM {batch // 2}) instead of 64"},
-            "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps of the 6-task schedule at batch {batch}, fp32 torch CPU autograd of oracle/hamt_oracle.py"},
+            "config": {"workload": conf["workload"], "global_batch": B, "per_gpu_batch": B, "itm_batch": B // 2, "parallelism": "cpu",
+                       "mode": "train (dropout 0.1)", "note": f"{what}, fp32 on the host cores; {warm} untimed warm-up steps"},
+            "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": threads, "kind": kind,
+                             "sample": f"{args.steps} steps of the task schedule at batch {B} (ITM {B // 2}), fwd+bwd, train mode, fp32 torch CPU, {threads} threads ({dt:.1f} s)"},
             "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if gpu_eager is not None:
-        line["gpu_eager_port"] = gpu_eager
+        line["gpu_eager_reference"] = gpu_eager
     print(json.dumps(line), flush=True)
 
 

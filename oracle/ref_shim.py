@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference modules (cshizhe/VLN-HAMT) under torch 2.11 / transformers 5.x.
 
-TEST INFRASTRUCTURE ONLY.  Works only where the reference checkout exists (this build container:
-/root/reference).  It never exists on the GPU box; everything that runs there uses the committed
-golden vectors produced through this shim by oracle/make_golden.py.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Needs the reference's Python sources: the checkout in the build container
+(/root/reference) or the verbatim copy `__graft_entry__.build()` installs under baseline/_ref (git-ignored; it
+travels to the GPU box with the snapshot, where it is what `bench.py --impl reference` times).  The GPU tests never
+import it: they use the committed golden vectors produced through this shim by oracle/make_golden.py.
 
 The shim follows SURVEY.md section 8c: the reference pins transformers==4.12.3
 (requirements.txt:11) and uses three things from it that transformers 5 removed/changed:
@@ -20,7 +21,19 @@ import sys
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("HAMT_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _resolve_root() -> str:
+    """The reference checkout (build container) or the verbatim copy of its Python sources that `__graft_entry__.build()` installs
+    under baseline/_ref (git-ignored; travels to the GPU box like the built .so)."""
+    for cand in (os.environ.get("HAMT_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO_ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "pretrain_src", "model", "vilmodel.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:

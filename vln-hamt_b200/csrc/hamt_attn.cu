@@ -507,6 +507,10 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   p.dq = (__nv_bfloat16*)a.dq; p.dk = (__nv_bfloat16*)a.dk; p.dv = (__nv_bfloat16*)a.dv;
   p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
   HAMT_REQUIRE((a.dbq == nullptr) == (a.dbk == nullptr) && (a.dbq == nullptr) == (a.dbv == nullptr), "attn_bwd: bias-gradient pointers come as a triple");
+  {
+    int rc = 0;
+    if (attn_bwd_tc(a, st, &rc)) return rc;      // TMA + tcgen05 packed-tile kernel; shapes outside its envelope fall through
+  }
   const int Sq_pad = (a.f.Sq + 15) & ~15, Sk_pad = (a.f.Sk + 15) & ~15;
   const bool is_long = Sq_pad > 128 || Sk_pad > 128;
   const size_t smem = (size_t)(2 * Sq_pad + 2 * Sk_pad) * LDS * 2 + (is_long ? 0 : (size_t)Sq_pad * (Sk_pad + 8) * 2) + (Sk_pad + 2 * Sq_pad + 3 * D) * 4;

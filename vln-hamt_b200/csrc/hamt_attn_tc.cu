@@ -486,6 +486,422 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
+// backward
+//
+//   S = Q K^T, dP = dO V^T                       (two MMAs into TMEM, same packed-tile layout as the forward)
+//   P = exp2(S c + mask - lse), Pd = P o drop, delta_i = sum_j Pd_ij dP_ij, dS = P o (dP o drop - delta) * scale     (one thread per query row)
+//   dV = Pd^T dO, dK = dS^T Q, dQ = dS K         (three MMAs; Pd / dS are written ONCE to shared memory as bf16 [query][key] tiles and
+//                                                 serve as K-major A operand for dQ and as MN-major A operand for dV / dK)
+// delta is computed from the recomputed probabilities (sum_j Pd_ij dP_ij = dO_i . O_i): the saved forward output is not read at all.
+// Warps 4..7 do the softmax backward of tile i + 1 while warps 8..11 drain / store the dQ, dK, dV accumulators of tile i.
+// Bias gradients of the projections (column sums of dQ / dK / dV per head):
+//   * value bias: sum_k dV[k,:] = sum_q (sum_k Pd[q,k]) dO[q,:] -- the row sums of Pd are thread-local, so they are written (as a bf16
+//     hi + lo pair) into two spare key slots of the packed key axis and the dV MMA itself produces the sums as two extra rows;
+//   * query bias: halving butterfly (62 shuffles per warp) over the fp32 dQ accumulator rows in the epilogue;
+//   * key bias: identically zero (rows of dS sum to zero: sum_j P_ij (dP_ij drop_ij - delta_i) = delta_i - delta_i): not accumulated.
+// dQ / dK / dV leave through plain 16-byte global stores, one full 128-byte row segment per lane (TMEM lane = row): a staged TMA
+// store needs shared memory the input ring cannot spare (two 64 KB stages + 64 KB of Pd / dS) or ties the stage release to the
+// store's completion -- measured 239 us against 203 us for the panorama shape (profiles/r02_attn_bwd_notes.txt).
+// Envelope: Sq <= 128 (one query tile per problem), packed key axis <= 128.
+// ------------------------------------------------------------------------------------------------------------------------------
+struct BwdParams {
+  Geom g;
+  int ns;
+  uint32_t stage_bytes, off_do, off_k, off_v;     // per input stage: Q at 0, dO, K, V
+  uint32_t off_pd, off_ds;                        // Pd / dS tiles (single), from the start of dynamic smem
+  uint32_t off_end;                               // end of the zero-initialised region (stages + Pd + dS)
+  int sum_slot;                                   // first of the 2 P spare key slots that carry the Pd row sums (hi, lo per problem)
+  uint32_t off_mask, mask_floats;                 // per softmax warp
+  uint32_t off_bar;
+  uint32_t tx_q32, tx_q8, tx_kv;
+  float scale_log2, scale;
+  const float* mask;
+  const float* lse;
+  float* dbq; float* dbv;                         // [heads * 64] fp32 or null
+  __nv_bfloat16 *dq, *dk, *dv;                    // outputs, q / k / v strides
+  long long q_bs, ldq, kv_bs, ldkv;
+  DropCfg drop;
+};
+
+// calls f(smem_byte_offset, small_box, first_query_row) for every row box of problem slot pi (the boxes the producer loads for Q / dO
+// and the epilogue stores for dQ)
+template <typename F>
+__device__ __forceinline__ void for_each_row_box(const Geom& g, int pi, F&& f) {
+  if (g.regime == 0) f((uint32_t)pi * 4096u, false, 0);
+  else if (g.regime == 1) { f((uint32_t)pi * 4096u, false, 0); f(96u * 128u + (uint32_t)pi * 1024u, true, 32); }
+  else if (g.regime == 2) { f((uint32_t)pi * 8192u, false, 0); if (g.Sq > 32) f((uint32_t)pi * 8192u + 4096u, false, 32); }
+  else { for (int k = 0; k < 4; ++k) if (k * 32 < g.Sq) f((uint32_t)k * 4096u, false, k * 32); }
+}
+
+template <int NU, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qr, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dor, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                   const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const Geom& g = p.g;
+  constexpr int NCH = (NU + 3) / 4;
+  constexpr int W = NU * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base + p.off_bar;
+  // barriers: full[ns], empty[ns], sdp_full, pds_full (4 warps), acc_full, acc_empty (4 warps), tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.ns + s); };
+  const uint32_t sdp_full = bar_base + 8u * (2 * p.ns), pds_full = sdp_full + 8, acc_full = sdp_full + 16, acc_empty = sdp_full + 24;
+  const uint32_t tmem_ptr_addr = sdp_full + 32;
+  if (warp == 0 && lane == 0) {
+    if (smem_base & 1023u) { printf("hamt attn bwd: dynamic smem base not 1024-byte aligned\n"); __trap(); }
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    for (int s = 0; s < p.ns; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_addr);
+  // everything that a TMA box may leave unwritten starts from zeros (finite garbage in unused operand rows / columns is harmless, NaN is not)
+  for (uint32_t i = threadIdx.x * 16u; i < p.off_end; i += kThreads * 16u) *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_grid_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  const int heads = g.heads;
+  const int n_my = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int kch = (g.n_total + 63) >> 6;
+  // TMEM columns: S 0, dP 128, dQ 256, dK 320, dV 384
+  constexpr uint32_t C_S = 0, C_DP = 128, C_DQ = 256, C_DK = 320, C_DV = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int s = i % p.ns;
+        mbar_wait(empty_bar(s), ((uint32_t)(i / p.ns) & 1u) ^ 1u);
+        const int p0 = tile * g.P, np = min(g.P, g.nprob - p0);
+        const uint32_t sq = smem_base + (uint32_t)s * p.stage_bytes, sdo = sq + p.off_do, sk = sq + p.off_k, sv = sq + p.off_v;
+        uint32_t bytes = 0;
+        for (int pi = 0; pi < np; ++pi) {
+          for_each_row_box(g, pi, [&](uint32_t, bool small, int) { bytes += 2 * (small ? p.tx_q8 : p.tx_q32); });
+          bytes += 2 * p.tx_kv;
+        }
+        mbar_expect_tx(full_bar(s), bytes);
+        for (int pi = 0; pi < np; ++pi) {
+          const int pr = p0 + pi, b = pr / heads, h = pr % heads;
+          for_each_row_box(g, pi, [&](uint32_t off, bool small, int q0) {
+            tma_load_3d(sq + off, small ? &tm_qr : &tm_q, h * 64, q0, b, full_bar(s));
+            tma_load_3d(sdo + off, small ? &tm_dor : &tm_do, h * 64, q0, b, full_bar(s));
+          });
+          tma_load_3d(sk + (uint32_t)(pi * W) * 128u, &tm_k, h * 64, 0, b, full_bar(s));
+          tma_load_3d(sv + (uint32_t)(pi * W) * 128u, &tm_v, h * 64, 0, b, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc_s = umma_idesc_bf16(128, g.n_total, false, false);    // S / dP: [128 q] x [n_total keys], both K-major (d contiguous)
+      const uint32_t idesc_kv = umma_idesc_bf16(128, 64, true, true);            // dV / dK: A = Pd / dS as [keys x q] (MN-major), B = dO / Q (MN-major)
+      const uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);            // dQ: A = dS [q x keys] K-major, B = K (MN-major)
+      const uint32_t spd = smem_base + p.off_pd, sds = smem_base + p.off_ds;
+      int a_i = 0, b_i = 0;            // next tile for phase A (S, dP) / phase B (dV, dK, dQ)
+      unsigned long long t0 = 0;
+      uint32_t idle = 0;
+      while (b_i < n_my) {
+        bool progressed = false;
+        // phase A of tile a_i: at most one tile ahead of phase B (letting it overtake phase B of the previous tile measured slower:
+        // 333 vs 279 us, profiles/r02_attn_bwd_notes.txt); the S / dP columns are free once Pd / dS of the previous tile exist
+        if (a_i < n_my && a_i <= b_i) {
+          const int st = a_i % p.ns;
+          if ((a_i == 0 || mbar_test_wait(pds_full, (uint32_t)(a_i - 1) & 1u)) && mbar_test_wait(full_bar(st), (uint32_t)(a_i / p.ns) & 1u)) {
+            tc_fence_after();
+            const uint32_t sq = smem_base + (uint32_t)st * p.stage_bytes, sdo = sq + p.off_do, sk = sq + p.off_k, sv = sq + p.off_v;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + C_S, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + C_DP, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+            ++a_i;
+            progressed = true;
+          }
+        }
+        // phase B of tile b_i: Pd / dS published (and S / dP read), accumulators of the previous tile drained
+        if (b_i < a_i && mbar_test_wait(pds_full, (uint32_t)b_i & 1u) && mbar_test_wait(acc_empty, ((uint32_t)b_i & 1u) ^ 1u)) {
+          tc_fence_after();
+          const int st = b_i % p.ns;
+          const uint32_t sq = smem_base + (uint32_t)st * p.stage_bytes, sdo = sq + p.off_do, sk = sq + p.off_k;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {          // reduction over the 128 query rows, 16 per step
+            const uint64_t da = umma_smem_desc(spd + (uint32_t)k * 2048u, 16384, 1024);
+            const uint64_t db = umma_smem_desc(sdo + (uint32_t)k * 2048u, 8192, 1024);
+            umma_bf16(tmem_base + C_DV, da, db, idesc_kv, k > 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = umma_smem_desc(sds + (uint32_t)k * 2048u, 16384, 1024);
+            const uint64_t db = umma_smem_desc(sq + (uint32_t)k * 2048u, 8192, 1024);
+            umma_bf16(tmem_base + C_DK, da, db, idesc_kv, k > 0 ? 1u : 0u);
+          }
+          const int ksteps = g.n_total >> 4;
+          for (int k = 0; k < ksteps; ++k) {     // reduction over the packed key axis
+            const uint64_t da = umma_smem_desc(sds + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u, 16, 1024);
+            const uint64_t db = umma_smem_desc(sk + (uint32_t)k * 2048u, 8192, 1024);
+            umma_bf16(tmem_base + C_DQ, da, db, idesc_q, k > 0 ? 1u : 0u);
+          }
+          umma_commit(acc_full);
+          umma_commit(empty_bar(st));          // Q / dO / K / V of this stage are no longer needed
+          ++b_i;
+          progressed = true;
+        }
+        if (progressed) idle = 0;
+        else if ((++idle & 0xfffu) == 0) {
+          if (t0 == 0) t0 = globaltimer_ns();
+          else if (globaltimer_ns() - t0 > 4000000000ull) { printf("hamt attn bwd: MMA issuer stalled (block %d a %d b %d of %d)\n", blockIdx.x, a_i, b_i, n_my); __trap(); }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== softmax backward: Pd, dS =====================
+    const int slot = warp & 3;
+    const AttnDrop ds = attn_drop_init(p.drop);
+    const bool multi = MULTI && slot == 3;
+    float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)(slot * p.mask_floats);
+    const int row = slot * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
+    uint8_t* pd_row = smem_raw + p.off_pd + (uint32_t)row * 128u;
+    uint8_t* ds_row = smem_raw + p.off_ds + (uint32_t)row * 128u;
+    const uint32_t rx = (uint32_t)(row & 7);
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int p0 = tile * g.P;
+      const RowMap rm = row_map(g, slot, lane, 0);
+      const int pr = p0 + rm.pi;
+      const bool valid = rm.ok && pr < g.nprob;
+      const float lse2 = valid ? p.lse[(long long)pr * g.Sq + rm.qrow] * 1.4426950408889634f : 0.f;
+      if (p.mask_floats != 0) {
+        const int nw = multi ? g.nwin : 1;
+        for (int wdx = 0; wdx < nw; ++wdx) {
+          const int prw = multi ? p0 + wdx : __shfl_sync(0xffffffffu, pr, 0);
+          const bool okw = multi ? (prw < g.nprob) : __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
+          const int bw = okw ? prw / heads : 0;
+          for (int j = lane; j < NCH * 32; j += 32) {
+            float mv = -INFINITY;
+            if (j < g.Sk) mv = okw ? p.mask[(long long)bw * g.Sk + j] * 1.4426950408889634f : 0.f;
+            smask[wdx * NCH * 32 + j] = mv;
+          }
+        }
+        __syncwarp();
+      }
+      mbar_wait(sdp_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_field + C_S, t_dp = tmem_base + lane_field + C_DP;
+      const int wpi = __shfl_sync(0xffffffffu, valid ? rm.pi : 0, 0);
+      // window loader: group pair (16 columns) c of S or dP for this lane (remainder warp: pick the lane's window out of three)
+      auto load16 = [&](uint32_t tbase, int c, uint32_t (&out)[16]) {
+        if (!MULTI || !multi) {
+          if (c + 16 <= NU * 8) tmem_ld_x16(tbase + (uint32_t)(wpi * W + c), out); else tmem_ld_x8(tbase + (uint32_t)(wpi * W + c), out);
+          tmem_ld_wait();
+        } else {
+          uint32_t t0[16], t1[16], t2[16];
+          if (c + 16 <= NU * 8) { tmem_ld_x16(tbase + 0 * W + c, t0); tmem_ld_x16(tbase + 1 * W + c, t1); tmem_ld_x16(tbase + 2 * W + c, t2); }
+          else { tmem_ld_x8(tbase + 0 * W + c, t0); tmem_ld_x8(tbase + 1 * W + c, t1); tmem_ld_x8(tbase + 2 * W + c, t2); }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) out[j] = rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j]);
+        }
+      };
+      // ---- pass 1: probabilities (kept in registers; the sign bit marks a dropped entry) and delta
+      float pv[NU * 8];
+      float delta = 0.f;
+      const uint32_t rowkey = attn_drop_rowkey(ds, (unsigned long long)pr * g.Sq + rm.qrow);
+      const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
+#pragma unroll
+      for (int c = 0; c < NU * 8; c += 16) {
+        uint32_t s16[16], d16[16];
+        load16(t_s, c, s16);
+        load16(t_dp, c, d16);
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          if (c + j < NU * 8) {
+            float ta, tb;
+            if (p.mask_floats != 0) {
+              ta = fmaf(__uint_as_float(s16[j]), p.scale_log2, mrow[c + j]) - lse2;
+              tb = fmaf(__uint_as_float(s16[j + 1]), p.scale_log2, mrow[c + j + 1]) - lse2;
+            } else {
+              ta = (c + j < g.Sk) ? fmaf(__uint_as_float(s16[j]), p.scale_log2, -lse2) : -INFINITY;
+              tb = (c + j + 1 < g.Sk) ? fmaf(__uint_as_float(s16[j + 1]), p.scale_log2, -lse2) : -INFINITY;
+            }
+            float pa = ex2_approx(ta), pb = ex2_approx(tb);
+            float ma = 1.f, mb = 1.f;
+            if (ds.on) {
+              const uint32_t bits = attn_drop_bits(rowkey, (uint32_t)((c + j) >> 1));
+              ma = (bits & 0xffffu) < ds.thresh16 ? 0.f : ds.scale;
+              mb = (bits >> 16) < ds.thresh16 ? 0.f : ds.scale;
+            }
+            delta = fmaf(pa * ma, __uint_as_float(d16[j]), delta);
+            delta = fmaf(pb * mb, __uint_as_float(d16[j + 1]), delta);
+            pv[c + j] = ma == 0.f ? -pa : pa;
+            pv[c + j + 1] = mb == 0.f ? -pb : pb;
+          }
+        }
+      }
+      // Pd / dS tiles are read by the MMAs of the previous tile until acc_full
+      if (i > 0) mbar_wait(acc_full, (uint32_t)(i - 1) & 1u);
+      // ---- pass 2: dS, and both rows to shared memory (zeros outside the lane's key window)
+      {
+        const int units = kch * 8;
+        const int u0 = valid ? rm.pi * NU : units;
+        auto unit_off = [&](int u) { return (uint32_t)(u >> 3) * 16384u + ((((uint32_t)u & 7u) ^ rx) << 4); };
+        const int us = p.sum_slot >> 3;                  // the 16-byte unit that holds the row-sum slots of all problems
+        for (int u = 0; u < u0; ++u) { *reinterpret_cast<uint4*>(pd_row + unit_off(u)) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(ds_row + unit_off(u)) = make_uint4(0, 0, 0, 0); }
+        for (int u = u0 + NU; u < units; ++u) { if (u != us || !valid) *reinterpret_cast<uint4*>(pd_row + unit_off(u)) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(ds_row + unit_off(u)) = make_uint4(0, 0, 0, 0); }
+        float rs = 0.f;                                  // sum_k Pd[row, k] (of the bf16-rounded values the dV MMA reads)
+        // (the TMEM loads are warp-collective: every lane issues them, only the arithmetic and the stores depend on `valid`)
+        const float dscale = ds.scale;
+#pragma unroll
+        for (int c = 0; c < NU * 8; c += 16) {
+          uint32_t d16[16];
+          load16(t_dp, c, d16);
+          if (valid) {
+#pragma unroll
+            for (int h8 = 0; h8 < 16; h8 += 8) {
+              if (c + h8 < NU * 8) {
+                float pdv[8], dsv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float pj = pv[c + h8 + e];
+                  const float pa = fabsf(pj);
+                  const float m = pj < 0.f ? 0.f : dscale;        // (exact zero probabilities carry no sign: pd = 0 either way)
+                  pdv[e] = pa * m;
+                  rs += bf16_round(pdv[e]);
+                  dsv[e] = pa * (__uint_as_float(d16[h8 + e]) * m - delta) * p.scale;
+                }
+                const uint32_t off = unit_off(u0 + ((c + h8) >> 3));
+                *reinterpret_cast<uint4*>(pd_row + off) = make_uint4(pack_bf16(pdv[0], pdv[1]), pack_bf16(pdv[2], pdv[3]), pack_bf16(pdv[4], pdv[5]), pack_bf16(pdv[6], pdv[7]));
+                *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]), pack_bf16(dsv[4], dsv[5]), pack_bf16(dsv[6], dsv[7]));
+              }
+            }
+          }
+        }
+        if (valid) {
+          // value-bias gradient through the dV MMA: Pd[row, sum_slot + 2 pi] = hi(rs), [.. + 1] = lo(rs); zeros for the other problems
+          const float hi = bf16_round(rs), lo = rs - hi;
+          const uint32_t pair = pack_bf16(hi, lo);
+          uint4 w = make_uint4(0, 0, 0, 0);
+          if (rm.pi == 0) w.x = pair; else if (rm.pi == 1) w.y = pair; else if (rm.pi == 2) w.z = pair; else w.w = pair;
+          *reinterpret_cast<uint4*>(pd_row + unit_off(us)) = w;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+  } else if (warp >= 8) {
+    // ===================== accumulators -> global: dQ, dK, dV (+ bias gradients) =====================
+    const int slot = warp & 3;
+    const int row = slot * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int p0 = tile * g.P, np = min(g.P, g.nprob - p0);
+      // destination rows of this lane: its query row (dQ) and its key of the packed key axis (dK, dV)
+      const RowMap rm = row_map(g, slot, lane, 0);
+      const bool q_ok = rm.ok && rm.pi < np;
+      const int kpi = row / W, key = row - kpi * W;
+      const bool k_ok = kpi < np && key < g.Sk;
+      __nv_bfloat16* gq = nullptr; __nv_bfloat16* gk = nullptr; __nv_bfloat16* gv = nullptr;
+      if (q_ok) { const int pr = p0 + rm.pi; gq = p.dq + (long long)(pr / heads) * p.q_bs + (long long)rm.qrow * p.ldq + (pr % heads) * 64; }
+      if (k_ok) {
+        const int pr = p0 + kpi;
+        const long long off = (long long)(pr / heads) * p.kv_bs + (long long)key * p.ldkv + (pr % heads) * 64;
+        gk = p.dk + off; gv = p.dv + off;
+      }
+      mbar_wait(acc_full, (uint32_t)i & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        uint32_t acc[64];         // one accumulator at a time: dQ, dK, dV
+        const uint32_t col = m == 0 ? C_DQ : (m == 1 ? C_DK : C_DV);
+        tmem_ld_x32(tmem_base + lane_field + col, &acc[0]);
+        tmem_ld_x32(tmem_base + lane_field + col + 32, &acc[32]);
+        tmem_ld_wait();
+        if (m == 2) {                                   // the last accumulator is in registers: the next tile's MMAs may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+        __nv_bfloat16* dst = m == 0 ? gq : (m == 1 ? gk : gv);
+        if (dst != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(dst + c * 8) =
+                make_uint4(pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1])), pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3])),
+                           pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5])), pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7])));
+        }
+        if (p.dbq != nullptr) {
+          if (m == 0) {
+            // query-bias gradient: column sums of this warp's 32 dQ rows (rows of no problem are exactly zero) by a halving
+            // butterfly; the remainder warp of the 3-problem layout stops after the 8-lane groups (one problem each)
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(acc[j]);
+            const bool h1 = lane & 1, h2 = lane & 2, h4 = lane & 4, h8 = lane & 8, h16 = lane & 16;
+            float w32[32], w16[16], w8[8];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w32[j] = (h1 ? v[32 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, h1 ? v[j] : v[32 + j], 1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w16[j] = (h2 ? w32[16 + j] : w32[j]) + __shfl_xor_sync(0xffffffffu, h2 ? w32[j] : w32[16 + j], 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w8[j] = (h4 ? w16[8 + j] : w16[j]) + __shfl_xor_sync(0xffffffffu, h4 ? w16[j] : w16[8 + j], 4);
+            // lane now holds 8 columns starting at c8, summed over its group of 8 rows
+            const int c8 = (h1 ? 32 : 0) + (h2 ? 16 : 0) + (h4 ? 8 : 0);
+            if (MULTI && slot == 3) {
+              const int pi = lane >> 3;
+              if (pi < np) {
+                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(bd + j, w8[j]);
+              }
+            } else {
+              float w4[4], w2[2];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) w4[j] = (h8 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[j] : w8[4 + j], 8);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) w2[j] = (h16 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, h16 ? w4[j] : w4[2 + j], 16);
+              int pi;
+              if (g.regime == 0 || g.regime == 1) pi = slot; else if (g.regime == 2) pi = slot >> 1; else pi = 0;
+              if (pi < np) {
+                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c8 + (h8 ? 4 : 0) + (h16 ? 2 : 0);
+                atomicAdd(bd, w2[0]);
+                atomicAdd(bd + 1, w2[1]);
+              }
+            }
+          } else if (m == 2) {
+            // value-bias gradient: the dV rows of the spare key slots hold sum_q rs_q dO[q,:] (hi and lo part)
+            const int k = row - p.sum_slot;
+            if (k >= 0 && k < 2 * np) {
+              float* bd = p.dbv + ((p0 + (k >> 1)) % heads) * 64;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) atomicAdd(bd + j, __uint_as_float(acc[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -522,7 +938,7 @@ static int make_map3(CUtensorMap* tm, const void* ptr, int B, int S, int heads, 
 }
 
 // packing plan for (Sq, Sk); max_ntotal bounds the packed key axis (forward: 192 with two warpgroups)
-static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal) {
+static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal, int spare_per_problem = 0) {
   g.nprob = B * heads; g.heads = heads; g.Sq = Sq; g.Sk = Sk;
   g.W = (Sk + 7) & ~7;
   if (g.W > 128) return false;                 // longer key axes: legacy kernel (RxR instructions)
@@ -531,14 +947,15 @@ static bool plan(Geom& g, int B, int heads, int Sq, int Sk, int max_ntotal) {
   else if (Sq <= 64) { g.regime = 2; g.P = 2; }
   else { g.regime = 3; g.P = 1; }
   // the packed key axis must fit the score tile; fall back to fewer problems per tile (regime 2 / 3 layouts)
-  while (g.P > 1 && ((g.P * g.W + 15) & ~15) > max_ntotal) {
+  auto ntot = [&](int P) { return (P * g.W + P * spare_per_problem + 15) & ~15; };
+  while (g.P > 1 && ntot(g.P) > max_ntotal) {
     if (g.regime == 1) { g.regime = 2; g.P = 2; }
     else if (g.regime == 0 && g.P == 4) { g.P = 2; }          // slots 0 and 1 only
     else if (g.regime == 0 && g.P == 2) { g.P = 1; }
     else { g.regime = 3; g.P = 1; }
   }
-  if (((g.P * g.W + 15) & ~15) > max_ntotal) return false;
-  g.n_total = (g.P * g.W + 15) & ~15;
+  if (ntot(g.P) > max_ntotal) return false;
+  g.n_total = ntot(g.P);
   g.QT = g.regime == 3 ? (Sq + 127) / 128 : 1;
   g.ntiles = ((g.nprob + g.P - 1) / g.P) * g.QT;
   g.nwin = g.regime == 1 ? 3 : 1;
@@ -610,6 +1027,56 @@ static int launch_fwd(const AttnArgs& a, const Geom& g, cudaStream_t st) {
   return check_launch("attn_fwd_tc_kernel");
 }
 
+template <int NU, bool MULTI>
+static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
+  constexpr int NCH = (NU + 3) / 4;
+  const AttnArgs& a = b.f;
+  BwdParams p{};
+  p.g = g;
+  const uint32_t krows = (uint32_t)g.n_total, kch = (uint32_t)(g.n_total + 63) / 64;
+  p.off_do = 16384u; p.off_k = 32768u; p.off_v = p.off_k + krows * 128u;
+  p.stage_bytes = p.off_v + krows * 128u;
+  p.mask_floats = a.mask != nullptr ? (uint32_t)(g.nwin * NCH * 32) : 0u;
+  // (a 64-key chunk of Pd read as MN-major A operand with M = 128 reaches one chunk past a 64-key tile: keep 2 chunks per tile)
+  const uint32_t tile_bytes = (kch < 2 ? 2u : kch) * 16384u;
+  const uint32_t fixed = 2 * tile_bytes + 4u * p.mask_floats * 4u + 256u;
+  int ns = (int)((232448u - 1024u - fixed) / p.stage_bytes);
+  if (ns > 4) ns = 4;
+  if (ns < 2) return 1;                                   // does not fit: the caller falls back to the legacy kernel
+  p.ns = ns;
+  p.off_pd = (uint32_t)ns * p.stage_bytes;
+  p.off_ds = p.off_pd + tile_bytes;
+  p.off_end = p.off_ds + tile_bytes;
+  p.off_mask = p.off_end;
+  p.off_bar = (p.off_mask + 4u * p.mask_floats * 4u + 15u) & ~15u;
+  p.sum_slot = g.P * g.W;
+  const size_t smem = p.off_bar + 256;
+  p.tx_q32 = 32 * 128; p.tx_q8 = 8 * 128; p.tx_kv = (uint32_t)g.W * 128u;
+  p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.mask = a.mask; p.lse = a.lse; p.dbq = b.dbq; p.dbv = b.dbv;
+  p.drop = DropCfg{a.drop.seed_ptr, a.drop.site, a.drop.p};
+  p.dq = (__nv_bfloat16*)b.dq; p.dk = (__nv_bfloat16*)b.dk; p.dv = (__nv_bfloat16*)b.dv;
+  p.q_bs = a.q_bstride; p.ldq = a.ldq; p.kv_bs = a.kv_bstride; p.ldkv = a.ldkv;
+  CUtensorMap tq, tqr, tdo, tdor, tk, tv;
+  int rc;
+  if ((rc = make_map3(&tq, a.q, a.B, a.Sq, a.heads, a.ldq, a.q_bstride, 32))) return rc;
+  if ((rc = make_map3(&tqr, a.q, a.B, a.Sq, a.heads, a.ldq, a.q_bstride, 8))) return rc;
+  if ((rc = make_map3(&tdo, b.dout, a.B, a.Sq, a.heads, b.lddo, b.do_bstride, 32))) return rc;
+  if ((rc = make_map3(&tdor, b.dout, a.B, a.Sq, a.heads, b.lddo, b.do_bstride, 8))) return rc;
+  if ((rc = make_map3(&tk, a.k, a.B, a.Sk, a.heads, a.ldkv, a.kv_bstride, g.W))) return rc;
+  if ((rc = make_map3(&tv, a.v, a.B, a.Sk, a.heads, a.ldkv, a.kv_bstride, g.W))) return rc;
+  auto kern = attn_bwd_tc_kernel<NU, MULTI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
+    attr_set = true;
+  }
+  const int grid = g.ntiles < num_sms_cached() ? g.ntiles : num_sms_cached();
+  launch_pdl(kern, grid, kThreads, smem, st, tq, tqr, tdo, tdor, tk, tv, p);
+  return check_launch("attn_bwd_tc_kernel");
+}
+
 }  // namespace tc
 
 void attn_set_impl(int v) { tc::g_attn_impl = v; }
@@ -641,6 +1108,43 @@ int attn_fwd_tc(const AttnArgs& a, cudaStream_t st, int* rc) {
       default: return 0;
     }
   }
+  return 1;
+}
+
+// backward: Sq <= 128 and a packed key axis of at most 128 keys (TMEM: S, dP, dQ, dK, dV = 448 of 512 columns)
+int attn_bwd_tc(const AttnBwdArgs& b, cudaStream_t st, int* rc) {
+  if (tc::g_attn_impl == 1) return 0;
+  const AttnArgs& a = b.f;
+  tc::Geom g;
+  if (a.Sq > 128 || !tc::plan(g, a.B, a.heads, a.Sq, a.Sk, 128, 2) || g.QT != 1) return 0;     // + 2 spare key slots per problem (Pd row sums)
+  // Dispatch by measurement (profiles/r02_kbench_attn_bwd.txt, profiles/r02_attn_bwd_notes.txt): with one tile in flight per SM
+  // (TMEM holds S, dP and three accumulators of ONE tile; shared memory two 64 KB input stages next to 64 KB of Pd / dS) this
+  // kernel beats the legacy one where two ~53-row problems share a tile (53 x 53: 24.8 vs 30.2 us) and for short key axes
+  // (80 x 16: 21.2 vs 26.9 us), and loses on the panorama shape (279 vs 215 us) and on 80-key problems (41 vs 33-38 us).
+  if (tc::g_attn_impl != 2) {
+    const bool wins = (g.regime == 2 && g.P == 2) || (g.regime == 3 && g.W <= 16);
+    if (!wins) return 0;
+  }
+  const int nu = g.W / 8;
+  int r = 1;
+  if (g.regime == 1) {
+    switch (nu) {
+#define HAMT_CASE(N_) case N_: r = tc::launch_bwd<N_, true>(b, g, st); break;
+      HAMT_CASE(1) HAMT_CASE(2) HAMT_CASE(3) HAMT_CASE(4) HAMT_CASE(5) HAMT_CASE(6) HAMT_CASE(7) HAMT_CASE(8)
+#undef HAMT_CASE
+      default: return 0;
+    }
+  } else {
+    switch (nu) {
+#define HAMT_CASE(N_) case N_: r = tc::launch_bwd<N_, false>(b, g, st); break;
+      HAMT_CASE(1) HAMT_CASE(2) HAMT_CASE(3) HAMT_CASE(4) HAMT_CASE(5) HAMT_CASE(6) HAMT_CASE(7) HAMT_CASE(8)
+      HAMT_CASE(9) HAMT_CASE(10) HAMT_CASE(11) HAMT_CASE(12) HAMT_CASE(13) HAMT_CASE(14) HAMT_CASE(15) HAMT_CASE(16)
+#undef HAMT_CASE
+      default: return 0;
+    }
+  }
+  if (r == 1) return 0;       // shared memory does not fit two stages: legacy kernel
+  *rc = r;
   return 1;
 }
 

@@ -55,6 +55,7 @@ struct AttnBwdArgs {
 int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 // tcgen05 / TMA kernels (hamt_attn_tc.cu): return 1 when they took the problem (status in *rc), 0 -> run the legacy kernel
 int attn_fwd_tc(const AttnArgs& a, cudaStream_t st, int* rc);
+int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st, int* rc);
 void attn_set_impl(int v);      // 0 = auto, 1 = legacy mma.sync kernels only
 
 // text embedding: out = drop(LN(word[ids] + pos[s] + type0))
