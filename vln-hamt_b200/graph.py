@@ -43,7 +43,7 @@ def add_sync_free_extras(task: str, batch: Dict, device=None) -> Dict:
         hm = b.get("_hist_masks_host")           # host copy kept next to a device-resident batch: no device->host sync
         if hm is None:
             hm = b["hist_masks"].cpu()
-        neg, shuf = itm_negative_plan(hm.shape[0], hm, b["hist_img_fts"].shape[1], 4)
+        neg, shuf = itm_negative_plan(hm.shape[0], hm, hm.shape[1] - 1, 4)        # hist_masks = CLS slot + T steps
         b["itm_plan"] = (neg, shuf)
     if device is not None:
         for k, v in list(b.items()):
