@@ -11,6 +11,7 @@ Block structure follows the reference modules:
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -31,6 +32,26 @@ def _as32(x16: torch.Tensor, x32: Optional[torch.Tensor]) -> torch.Tensor:
     return x32 if x32 is not None else x16.detach().float()
 
 
+# Weight-gradient GEMMs on a second stream.  dW = dY^T X only feeds the gradient buffer: nothing later in the backward pass reads
+# it, while the dgrad GEMM that consumes the same dY is on the critical path.  Every GEMM is a persistent grid holding all 148 SMs
+# (one ~200 KB CTA each), so two dependent launches never overlap: the measured cost of a launch is ~8 us on top of its
+# tensor-pipe time (pipeline fill, last-tile epilogue, grid drain; profiles/r02_bench_signatures_g.txt, intercept of time against
+# K at M = 5120) and there are ~260 GEMM launches per step.  With the wgrads forked onto a side stream the block scheduler places
+# their CTAs on the SMs the critical-path kernel frees while it drains (and vice versa), in eager mode and -- as parallel
+# branches -- inside the captured step graph.  The side stream is joined where a layer's gradients must be final (Run.done:
+# data-parallel hook) and at the end of the backward pass.  HAMT_WGRAD_STREAM=0 restores the single-stream order.
+WGRAD_SIDE_STREAM = os.environ.get("HAMT_WGRAD_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class Run:
     """Per-forward context: arena, mode, dropout probabilities and the dropout call-site counter."""
 
@@ -43,17 +64,76 @@ class Run:
         self.save = torch.is_grad_enabled()
         self._site = 0
         self.uses = {}
+        self._side = None           # side stream with wgrad work in flight (None: nothing to join)
+        self._side_refs = []        # operands of in-flight side-stream GEMMs (kept alive until retired: they were allocated on the main stream)
+        self._refs_total = 0        # operands ever appended / already retired (absolute counters)
+        self._refs_base = 0
+        self._marks = []            # (event on the side stream, _refs_total at that point, layer whose backward ended there)
+        self._join_queued = False
+
+    def fork_wgrad(self, fn, *keep):
+        """Run fn() (a weight-gradient GEMM) on the side stream, ordered after everything enqueued so far on the current stream."""
+        if not WGRAD_SIDE_STREAM:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        side = _side_stream(cur.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()
+        self._side = side
+        self._side_refs.append(keep)
+        self._refs_total += 1
+        if not self._join_queued:
+            # final join at the end of this backward pass (heads / embedders have no layer hook); inside a captured step this is
+            # also what re-joins the forked branch before the capture ends
+            self._join_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._final_join)
+
+    def _hook(self, layer):
+        hook = getattr(self.arena, "layer_hook", None)
+        if hook is not None and layer is not None:
+            hook(layer)
+
+    def _retire(self, mark):
+        ev, total, layer = mark
+        torch.cuda.current_stream().wait_event(ev)
+        del self._side_refs[:total - self._refs_base]
+        self._refs_base = total
+        self._hook(layer)           # the layer's weight gradients are final: data-parallel exchange may start
+
+    def join_side(self):
+        """Main stream waits for all forked weight-gradient work; pending layer hooks fire."""
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side = None
+            self._side_refs.clear()
+            self._refs_base = self._refs_total
+        marks, self._marks = self._marks, []
+        for _, _, layer in marks:
+            self._hook(layer)
+
+    def _final_join(self):
+        self._join_queued = False
+        self.join_side()
 
     def used(self, layer):
         self.uses[id(layer)] = self.uses.get(id(layer), 0) + 1
 
     def done(self, layer):
-        """Called at the end of a layer's backward; fires the data-parallel hook once its gradients are final."""
+        """Called at the end of a layer's backward.  Its weight gradients come from the side stream, so the layer is retired
+        (operands released, data-parallel hook fired) one layer later, when waiting for them costs nothing."""
         n = self.uses.get(id(layer), 1) - 1
         self.uses[id(layer)] = n
-        hook = getattr(self.arena, "layer_hook", None)
-        if n == 0 and hook is not None:
-            hook(layer)
+        if self._side is None:
+            if n == 0:
+                self._hook(layer)
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        self._marks.append((ev, self._refs_total, layer if n == 0 else None))
+        if len(self._marks) > 1:
+            self._retire(self._marks.pop(0))
 
     def drop(self, module_or_p) -> ops.Drop:
         p = module_or_p if isinstance(module_or_p, float) else float(module_or_p.p)
@@ -63,10 +143,17 @@ class Run:
         return ops.Drop(self.seed if self.seed is not None else self.arena.seed, self._site, p)
 
 
-def _wgrad(A: ParamArena, dy: torch.Tensor, x: torch.Tensor, weight):
-    """weight.grad[N,K] += dy[M,N]^T x[M,K]  (both operands MN-major, fp32 split-K accumulation)."""
+def _wgrad(run: "Run", dy: torch.Tensor, x: torch.Tensor, weight):
+    """weight.grad[N,K] += dy[M,N]^T x[M,K]  (both operands MN-major, fp32 split-K accumulation), off the critical path."""
     if weight.requires_grad:
-        ops.gemm(dy, x, a_mn=True, b_mn=True, out=A.grad(weight), accumulate=True)
+        g = run.arena.grad(weight)
+        run.fork_wgrad(lambda: ops.gemm(dy, x, a_mn=True, b_mn=True, out=g, accumulate=True), dy, x)
+
+
+def _wgrad_fused(run: "Run", dy: torch.Tensor, x: torch.Tensor, ws):
+    """Same for the fused q/k/v weight block (adjacent in the arena)."""
+    g = run.arena.fused_grad(ws)
+    run.fork_wgrad(lambda: ops.gemm(dy, x, a_mn=True, b_mn=True, out=g, accumulate=True), dy, x)
 
 
 def _bgrad(A: ParamArena, dy: torch.Tensor, bias):
@@ -103,14 +190,14 @@ def attn_block_bwd(run: Run, dy, saved, att, out_mod, dx_out=None):
     ws, bs = _qkv_params(att)
     ln, dense = out_mod.LayerNorm, out_mod.dense
     dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid, dres_out=dx_out)
-    _wgrad(A, dt, ctx, dense.weight)
+    _wgrad(run, dt, ctx, dense.weight)
     dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
     dqkv = torch.empty_like(qkv)
     db = A.fused_grad(bs) if ws[0].requires_grad else None      # q/k/v bias gradients: column sums fused into the attention backward
     ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, S, S, run.heads,
                  mask, d_attn, dbias=db)
     if ws[0].requires_grad:
-        ops.gemm(dqkv, x, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
+        _wgrad_fused(run, dqkv, x, ws)
     ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)       # dx (residual path) += dqkv @ Wqkv
     return dx
 
@@ -142,11 +229,11 @@ def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
     ln = out_mod.LayerNorm
     w1, w2 = inter.dense.weight, out_mod.dense.weight
     dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(out_mod.dense.bias), drop=d_hid, dres_out=dx_out)
-    _wgrad(A, dt, a, w2)
+    _wgrad(run, dt, a, w2)
     b1 = inter.dense.bias
     dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h,
                   colsum=A.grad(b1) if (b1 is not None and b1.requires_grad) else None)     # bias gradient fused into the dgrad epilogue
-    _wgrad(A, dh, x, w1)
+    _wgrad(run, dh, x, w1)
     ops.gemm(dh, A.w16(w1), b_mn=True, out=dx, accumulate=True)
     return dx
 
@@ -192,7 +279,7 @@ def cross_block_bwd(run: Run, dy, saved, xatt):
     db = A.fused_grad(bs) if ws[0].requires_grad else None      # q/k/v bias gradients accumulate from both directions' backward kernels
     if lang_ca:
         dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid)
-        _wgrad(A, dt, ctx, dense.weight)
+        _wgrad(run, dt, ctx, dense.weight)
         dctx = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:ML, :H], qkv[ML:, H:2 * H], qkv[ML:, 2 * H:], ctx[:ML], lse_l, dctx[:ML], dqkv[:ML, :H], dqkv[ML:, H:2 * H],
@@ -203,13 +290,13 @@ def cross_block_bwd(run: Run, dy, saved, xatt):
         dx = torch.empty_like(xcat)
         dx[:ML].copy_(dy[:ML])
         dt, _ = ops.ln_bwd(dy[ML:], z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(dense.bias), drop=d_hid, dres_out=dx[ML:])
-        _wgrad(A, dt, ctx[ML:], dense.weight)
+        _wgrad(run, dt, ctx[ML:], dense.weight)
         dctx_v = ops.gemm(dt, A.w16(dense.weight), b_mn=True)
         dqkv = torch.zeros_like(qkv)
         ops.attn_bwd(qkv[ML:, :H], qkv[:ML, H:2 * H], qkv[:ML, 2 * H:], ctx[ML:], lse_v, dctx_v, dqkv[ML:, :H], dqkv[:ML, H:2 * H],
                      dqkv[:ML, 2 * H:], B, V, L, run.heads, lang_mask, d_att_v, dbias=db)
     if ws[0].requires_grad:
-        ops.gemm(dqkv, xcat, a_mn=True, b_mn=True, out=A.fused_grad(ws), accumulate=True)
+        _wgrad_fused(run, dqkv, xcat, ws)
     ops.gemm(dqkv, A.fused_w16(ws), b_mn=True, out=dx, accumulate=True)
     return dx
 
@@ -352,7 +439,7 @@ class LinearFn(torch.autograd.Function):
             dy = _mul_dact(dy, pre, ops.AUX_MUL_DGELU)
         elif act == ops.ACT_RELU:
             dy = _mul_dact(dy, pre, ops.AUX_MUL_DRELU)
-        _wgrad(A, dy, x, weight)
+        _wgrad(run, dy, x, weight)
         _bgrad(A, dy, bias)
         dx = ops.gemm(dy, A.w16(weight), b_mn=True) if ctx.need_dx else None
         ctx.x = ctx.pre = None
@@ -437,6 +524,7 @@ class TextEmbedFn(torch.autograd.Function):
     def backward(ctx, dy):
         A, emb = ctx.run.arena, ctx.emb
         dy = dy.to(BF16).contiguous()
+        ctx.run.join_side()         # the tied MLM decoder's weight gradient (side stream) lands in the word-embedding gradient too
         ops.embed_text_bwd(dy, ctx.ids, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
                            emb.LayerNorm.weight, A.grad(emb.word_embeddings.weight), A.grad(emb.position_embeddings.weight),
                            A.grad(emb.token_type_embeddings.weight)[0], A.grad(emb.LayerNorm.weight), A.grad(emb.LayerNorm.bias), ctx.run.eps,
@@ -480,7 +568,7 @@ class FeatEmbedFn(torch.autograd.Function):
         if ctx.kw["g_f"] is not None:
             grads["dg_f"], grads["db_f"] = A.grad(P["ln_f"].weight), A.grad(P["ln_f"].bias)
         dt, dextra = ops.embed_feat_bwd(dy, t, ang, *ctx.base, grads, eps=run.eps, drop=ctx.d, want_dextra=ctx.has_extra, **ctx.kw)
-        _wgrad(A, dt, x16, lin.weight)
+        _wgrad(run, dt, x16, lin.weight)
         ctx.saved = None
         return (None, dextra) + (None,) * 8
 
