@@ -134,3 +134,62 @@ def load_navcmt(cfg):
     """-> reference NavCMT (finetune_src/models/vilmodel_cmt.py:610)."""
     mod = _import_from("finetune_src", "models.vilmodel_cmt")
     return mod.NavCMT(cfg)
+
+
+# --------------------------------------------------------------------------------------------------------------------------
+# end-to-end stage (SURVEY f3): the reference's vision backbone is a vendored timm file that imports five helper names from
+# timm (vision_transformer.py:30-33); timm is not installed here.  The stand-ins below let the UNMODIFIED file import; none of
+# them contributes forward arithmetic (DropPath is only instantiated for drop_path > 0, the reference passes 0:
+# image_vilmodel.py:26-29; the init helpers only draw initial weights, which the tests overwrite with a seeded state_dict).
+# --------------------------------------------------------------------------------------------------------------------------
+def _install_timm_stubs():
+    import types
+    if "timm" in sys.modules and not getattr(sys.modules["timm"], "_hamt_stub", False):
+        return                                  # a real timm is importable: use it
+    def mod(name):
+        m = types.ModuleType(name)
+        m._hamt_stub = True
+        sys.modules[name] = m
+        return m
+    timm, data, models = mod("timm"), mod("timm.data"), mod("timm.models")
+    helpers, layers, registry = mod("timm.models.helpers"), mod("timm.models.layers"), mod("timm.models.registry")
+    timm.data, timm.models = data, models
+    models.helpers, models.layers, models.registry = helpers, layers, registry
+    data.IMAGENET_DEFAULT_MEAN, data.IMAGENET_DEFAULT_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    helpers.build_model_with_cfg = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("timm stub: build the class directly"))
+    helpers.overlay_external_default_cfg = lambda cfg, kw: cfg
+
+    class DropPath(nn.Module):                  # never instantiated with drop_path = 0 (vision_transformer.py:190)
+        def __init__(self, p=0.0):
+            super().__init__()
+            if p:
+                raise RuntimeError("timm stub: stochastic depth is not part of the HAMT path (drop_path_rate = 0)")
+
+        def forward(self, x):
+            return x
+
+    layers.DropPath = DropPath
+    layers.to_2tuple = lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+    layers.trunc_normal_ = lambda t, std=1.0, **k: nn.init.trunc_normal_(t, std=std, a=-2 * std, b=2 * std)
+    layers.lecun_normal_ = lambda t: nn.init.normal_(t, std=(1.0 / t.shape[1]) ** 0.5 if t.dim() > 1 else 1.0)
+    registry.register_model = lambda fn: fn
+
+
+def load_reference_vit(depth: int = 12, drop_rate: float = 0.0, attn_drop_rate: float = 0.0, **kw):
+    """-> the reference's VisionTransformer (pretrain_src/model/vision_transformer.py:226) at ViT-B/16 geometry
+    (vit_base_patch16_224 :507-513: patch 16, embed 768, heads 12; `depth` may be reduced for small fixtures), num_classes = 0."""
+    _install_timm_stubs()
+    if not reference_available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True
+    import importlib.util
+    path = os.path.join(REFERENCE_ROOT, "pretrain_src", "model", "vision_transformer.py")
+    key = ("file", path)
+    if key not in _LOADED:
+        spec = importlib.util.spec_from_file_location("hamt_ref_vision_transformer", path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _LOADED[key] = m
+    vt = _LOADED[key]
+    return vt.VisionTransformer(patch_size=16, embed_dim=768, depth=depth, num_heads=12, num_classes=0, drop_rate=drop_rate,
+                                attn_drop_rate=attn_drop_rate, drop_path_rate=0.0, **kw)

@@ -69,14 +69,14 @@ def main():
     # attention (pano / text / cross / vision shapes of the batch-64 step, plus the 16-token history-only shapes of MLM / MRC / ITM)
     from hamt_b200 import _lib
     for (B, Sq, Sk) in [(960, 36, 36), (64, 80, 80), (64, 80, 53), (64, 53, 80), (64, 53, 53), (64, 16, 80), (64, 80, 16), (64, 16, 16), (2560, 36, 36)]:
-      for legacy in ((1, 0) if "--attn-ab" in sys.argv else (0,)):
+      for legacy in ((1, 2) if "--attn-ab" in sys.argv else (0,)):       # 1 = legacy mma.sync kernels, 2 = tcgen05 forced wherever it fits, 0 = shipped dispatch
         _lib.load().hamt_attn_set_impl(legacy)
         qkv = torch.randn(B * max(Sq, Sk), 2304, device="cuda").to(torch.bfloat16)
         q, k, v = qkv[:B * Sq, :768], qkv[:B * Sk, 768:1536], qkv[:B * Sk, 1536:]
         if "--attn-drop" in sys.argv:
             drop = ops.Drop(torch.tensor([1], dtype=torch.int64, device="cuda"), 1, 0.1)
             t = timeit(lambda: ops.attn_fwd(q, k, v, B, Sq, Sk, 12, None, drop))
-            print(json.dumps({"attn_dropout": [B, Sq, Sk], "impl": "legacy" if legacy else "tcgen05", "fwd_us": round(t * 1e3, 1)}), flush=True)
+            print(json.dumps({"attn_dropout": [B, Sq, Sk], "impl": {0: "auto", 1: "legacy", 2: "tcgen05"}[legacy], "fwd_us": round(t * 1e3, 1)}), flush=True)
         t = timeit(lambda: ops.attn_fwd(q, k, v, B, Sq, Sk, 12, None))
         out, lse = ops.attn_fwd(q, k, v, B, Sq, Sk, 12, None)
         dout = torch.randn_like(out)
@@ -84,7 +84,7 @@ def main():
         t2 = timeit(lambda: ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:B * Sq, :768], dqkv[:B * Sk, 768:1536], dqkv[:B * Sk, 1536:], B, Sq, Sk, 12, None))
         db = torch.zeros(2304, device="cuda")
         t3 = timeit(lambda: ops.attn_bwd(q, k, v, out, lse, dout, dqkv[:B * Sq, :768], dqkv[:B * Sk, 768:1536], dqkv[:B * Sk, 1536:], B, Sq, Sk, 12, None, dbias=db))
-        print(json.dumps({"attn": [B, Sq, Sk], "impl": "legacy" if legacy else "tcgen05", "fwd_us": round(t * 1e3, 1), "bwd_us": round(t2 * 1e3, 1),
+        print(json.dumps({"attn": [B, Sq, Sk], "impl": {0: "auto", 1: "legacy", 2: "tcgen05"}[legacy], "fwd_us": round(t * 1e3, 1), "bwd_us": round(t2 * 1e3, 1),
                           "bwd_dbias_us": round(t3 * 1e3, 1), "fwd_GBs": round((B * (Sq + 2 * Sk) * 768 * 2 + B * Sq * 768 * 2) / t / 1e6, 1),
                           "bwd_GBs": round((B * (2 * Sq + 2 * Sk) * 768 * 2 + B * (Sq + 2 * Sk) * 768 * 2) / t3 / 1e6, 1)}), flush=True)
     _lib.load().hamt_attn_set_impl(0)

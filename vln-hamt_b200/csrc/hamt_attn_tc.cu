@@ -37,7 +37,9 @@ namespace hamt {
 
 namespace tc {
 
-static constexpr int kThreads = 384;     // warps 0..3: TMA producer, MMA issuer, 2 spare; warps 4..7 and 8..11: the two softmax warpgroups
+static constexpr int kThreads = 384;     // forward: warps 0..3: TMA producer, MMA issuer, 2 spare; warps 4..7 and 8..11: the two softmax warpgroups
+static constexpr int kBwdSoftmaxWarps = 16;                           // backward: warps 4..19 softmax backward (4 per TMEM lane quarter), 20..23 epilogue
+static constexpr int kBwdThreads = (4 + kBwdSoftmaxWarps + 4) * 32;   // 768
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -512,6 +514,7 @@ struct BwdParams {
   uint32_t off_end;                               // end of the zero-initialised region (stages + Pd + dS)
   int sum_slot;                                   // first of the 2 P spare key slots that carry the Pd row sums (hi, lo per problem)
   uint32_t off_mask, mask_floats;                 // per softmax warp
+  uint32_t off_xch;                               // fp32 [2][4][128]: per-part partial delta / Pd row sums of the tile rows
   uint32_t off_bar;
   uint32_t tx_q32, tx_q8, tx_kv;
   float scale_log2, scale;
@@ -534,7 +537,7 @@ __device__ __forceinline__ void for_each_row_box(const Geom& g, int pi, F&& f) {
 }
 
 template <int NU, bool MULTI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qr, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dor, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                    const BwdParams p) {
@@ -545,7 +548,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   constexpr int W = NU * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_base = smem_base + p.off_bar;
-  // barriers: full[ns], empty[ns], sdp_full, pds_full (4 warps), acc_full, acc_empty (4 warps), tmem ptr
+  // barriers: full[ns], empty[ns], sdp_full, pds_full (16 softmax warps), acc_full, acc_empty (4 epilogue warps), tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.ns + s); };
   const uint32_t sdp_full = bar_base + 8u * (2 * p.ns), pds_full = sdp_full + 8, acc_full = sdp_full + 16, acc_empty = sdp_full + 24;
@@ -554,12 +557,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (smem_base & 1023u) { printf("hamt attn bwd: dynamic smem base not 1024-byte aligned\n"); __trap(); }
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     for (int s = 0; s < p.ns; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, kBwdSoftmaxWarps); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr_addr);
   // everything that a TMA box may leave unwritten starts from zeros (finite garbage in unused operand rows / columns is harmless, NaN is not)
-  for (uint32_t i = threadIdx.x * 16u; i < p.off_end; i += kThreads * 16u) *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x * 16u; i < p.off_end; i += kBwdThreads * 16u) *reinterpret_cast<uint4*>(smem_raw + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -664,12 +667,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + kBwdSoftmaxWarps) {
     // ===================== softmax backward: Pd, dS =====================
+    // 16 warps: warp = 4 + 4 * part + quarter.  The four warps of a quarter own the same 32 tile rows (TMEM lanes) and split the
+    // key window of a row into four runs of 8-key units, so a thread handles at most MU = ceil(NU / 4) units.  With one thread per
+    // whole row (4 warps, one per scheduler) the ~2300 dependent instructions of a row ran at 0.2 IPC and bounded the kernel
+    // (profiles/r02_attn_bwd_notes.txt); the row-wide quantities (delta, the Pd row sum) now cross the four warps once per tile
+    // through shared memory and a 128-thread named barrier.
+    constexpr int MU = (NU + 3) / 4;
     const int slot = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int ub = (part * NU) >> 2, ue = ((part + 1) * NU) >> 2;       // this thread's units of the key window
     const AttnDrop ds = attn_drop_init(p.drop);
     const bool multi = MULTI && slot == 3;
-    float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)(slot * p.mask_floats);
+    float* smask = reinterpret_cast<float*>(smem_raw + p.off_mask) + (uint32_t)((warp - 4) * p.mask_floats);
+    float* xch = reinterpret_cast<float*>(smem_raw + p.off_xch);       // [2][4 parts][128 rows]: partial delta, partial Pd row sum
     const int row = slot * 32 + lane;
     const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
     uint8_t* pd_row = smem_raw + p.off_pd + (uint32_t)row * 128u;
@@ -688,7 +700,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const int prw = multi ? p0 + wdx : __shfl_sync(0xffffffffu, pr, 0);
           const bool okw = multi ? (prw < g.nprob) : __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
           const int bw = okw ? prw / heads : 0;
-          for (int j = lane; j < NCH * 32; j += 32) {
+          for (int j = ub * 8 + lane; j < ue * 8; j += 32) {
             float mv = -INFINITY;
             if (j < g.Sk) mv = okw ? p.mask[(long long)bw * g.Sk + j] * 1.4426950408889634f : 0.f;
             smask[wdx * NCH * 32 + j] = mv;
@@ -700,55 +712,64 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
       const uint32_t t_s = tmem_base + lane_field + C_S, t_dp = tmem_base + lane_field + C_DP;
       const int wpi = __shfl_sync(0xffffffffu, valid ? rm.pi : 0, 0);
-      // window loader: group pair (16 columns) c of S or dP for this lane (remainder warp: pick the lane's window out of three)
-      auto load16 = [&](uint32_t tbase, int c, uint32_t (&out)[16]) {
+      // unit loader: 8 columns of S or dP at column c of this lane's key window (remainder warp: pick the lane's window out of three)
+      auto load8 = [&](uint32_t tbase, int c, uint32_t (&out)[8]) {
         if (!MULTI || !multi) {
-          if (c + 16 <= NU * 8) tmem_ld_x16(tbase + (uint32_t)(wpi * W + c), out); else tmem_ld_x8(tbase + (uint32_t)(wpi * W + c), out);
-          tmem_ld_wait();
+          tmem_ld_x8(tbase + (uint32_t)(wpi * W + c), out);
         } else {
-          uint32_t t0[16], t1[16], t2[16];
-          if (c + 16 <= NU * 8) { tmem_ld_x16(tbase + 0 * W + c, t0); tmem_ld_x16(tbase + 1 * W + c, t1); tmem_ld_x16(tbase + 2 * W + c, t2); }
-          else { tmem_ld_x8(tbase + 0 * W + c, t0); tmem_ld_x8(tbase + 1 * W + c, t1); tmem_ld_x8(tbase + 2 * W + c, t2); }
+          uint32_t t0[8], t1[8], t2[8];
+          tmem_ld_x8(tbase + 0 * W + c, t0); tmem_ld_x8(tbase + 1 * W + c, t1); tmem_ld_x8(tbase + 2 * W + c, t2);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) out[j] = rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j]);
+          for (int j = 0; j < 8; ++j) out[j] = rm.pi == 0 ? t0[j] : (rm.pi == 1 ? t1[j] : t2[j]);
         }
       };
-      // ---- pass 1: probabilities (kept in registers; the sign bit marks a dropped entry) and delta
-      float pv[NU * 8];
-      float delta = 0.f;
+      // ---- pass 1: probabilities (kept in registers; the sign bit marks a dropped entry), partial delta and partial Pd row sum
+      float pv[MU * 8];
+      float delta = 0.f, rs = 0.f;
       const uint32_t rowkey = attn_drop_rowkey(ds, (unsigned long long)pr * g.Sq + rm.qrow);
       const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
+      const float dscale = ds.scale;
 #pragma unroll
-      for (int c = 0; c < NU * 8; c += 16) {
-        uint32_t s16[16], d16[16];
-        load16(t_s, c, s16);
-        load16(t_dp, c, d16);
+      for (int k = 0; k < MU; ++k) {
+        const int u = ub + k;
+        if (u < ue) {             // warp-uniform
+          const int c = u * 8;
+          uint32_t s8[8], d8[8];
+          load8(t_s, c, s8);
+          load8(t_dp, c, d8);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          if (c + j < NU * 8) {
+          for (int j = 0; j < 8; j += 2) {
             float ta, tb;
             if (p.mask_floats != 0) {
-              ta = fmaf(__uint_as_float(s16[j]), p.scale_log2, mrow[c + j]) - lse2;
-              tb = fmaf(__uint_as_float(s16[j + 1]), p.scale_log2, mrow[c + j + 1]) - lse2;
+              ta = fmaf(__uint_as_float(s8[j]), p.scale_log2, mrow[c + j]) - lse2;
+              tb = fmaf(__uint_as_float(s8[j + 1]), p.scale_log2, mrow[c + j + 1]) - lse2;
             } else {
-              ta = (c + j < g.Sk) ? fmaf(__uint_as_float(s16[j]), p.scale_log2, -lse2) : -INFINITY;
-              tb = (c + j + 1 < g.Sk) ? fmaf(__uint_as_float(s16[j + 1]), p.scale_log2, -lse2) : -INFINITY;
+              ta = (c + j < g.Sk) ? fmaf(__uint_as_float(s8[j]), p.scale_log2, -lse2) : -INFINITY;
+              tb = (c + j + 1 < g.Sk) ? fmaf(__uint_as_float(s8[j + 1]), p.scale_log2, -lse2) : -INFINITY;
             }
-            float pa = ex2_approx(ta), pb = ex2_approx(tb);
+            const float pa = ex2_approx(ta), pb = ex2_approx(tb);
             float ma = 1.f, mb = 1.f;
             if (ds.on) {
               const uint32_t bits = attn_drop_bits(rowkey, (uint32_t)((c + j) >> 1));
-              ma = (bits & 0xffffu) < ds.thresh16 ? 0.f : ds.scale;
-              mb = (bits >> 16) < ds.thresh16 ? 0.f : ds.scale;
+              ma = (bits & 0xffffu) < ds.thresh16 ? 0.f : dscale;
+              mb = (bits >> 16) < ds.thresh16 ? 0.f : dscale;
             }
-            delta = fmaf(pa * ma, __uint_as_float(d16[j]), delta);
-            delta = fmaf(pb * mb, __uint_as_float(d16[j + 1]), delta);
-            pv[c + j] = ma == 0.f ? -pa : pa;
-            pv[c + j + 1] = mb == 0.f ? -pb : pb;
+            const float pda = pa * ma, pdb = pb * mb;
+            delta = fmaf(pda, __uint_as_float(d8[j]), delta);
+            delta = fmaf(pdb, __uint_as_float(d8[j + 1]), delta);
+            rs += bf16_round(pda) + bf16_round(pdb);        // sum of the bf16-rounded values the dV MMA reads
+            pv[k * 8 + j] = ma == 0.f ? -pa : pa;
+            pv[k * 8 + j + 1] = mb == 0.f ? -pb : pb;
           }
         }
       }
+      // ---- the row's delta and Pd row sum: partials of the four column parts through shared memory
+      xch[part * 128 + row] = delta;
+      xch[512 + part * 128 + row] = rs;
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + slot) : "memory");
+      delta = (xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]);
       // Pd / dS tiles are read by the MMAs of the previous tile until acc_full
       if (i > 0) mbar_wait(acc_full, (uint32_t)(i - 1) & 1u);
       // ---- pass 2: dS, and both rows to shared memory (zeros outside the lane's key window)
@@ -757,39 +778,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int u0 = valid ? rm.pi * NU : units;
         auto unit_off = [&](int u) { return (uint32_t)(u >> 3) * 16384u + ((((uint32_t)u & 7u) ^ rx) << 4); };
         const int us = p.sum_slot >> 3;                  // the 16-byte unit that holds the row-sum slots of all problems
-        for (int u = 0; u < u0; ++u) { *reinterpret_cast<uint4*>(pd_row + unit_off(u)) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(ds_row + unit_off(u)) = make_uint4(0, 0, 0, 0); }
-        for (int u = u0 + NU; u < units; ++u) { if (u != us || !valid) *reinterpret_cast<uint4*>(pd_row + unit_off(u)) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(ds_row + unit_off(u)) = make_uint4(0, 0, 0, 0); }
-        float rs = 0.f;                                  // sum_k Pd[row, k] (of the bf16-rounded values the dV MMA reads)
+        // zero fill of the units outside the row's own window, shared out over the four parts
+        for (int u = part; u < units; u += 4) {
+          if (u >= u0 && u < u0 + NU) continue;
+          if (u != us || !valid) *reinterpret_cast<uint4*>(pd_row + unit_off(u)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(ds_row + unit_off(u)) = make_uint4(0, 0, 0, 0);
+        }
         // (the TMEM loads are warp-collective: every lane issues them, only the arithmetic and the stores depend on `valid`)
-        const float dscale = ds.scale;
 #pragma unroll
-        for (int c = 0; c < NU * 8; c += 16) {
-          uint32_t d16[16];
-          load16(t_dp, c, d16);
-          if (valid) {
+        for (int k = 0; k < MU; ++k) {
+          const int u = ub + k;
+          if (u < ue) {
+            uint32_t d8[8];
+            load8(t_dp, u * 8, d8);
+            tmem_ld_wait();
+            if (valid) {
+              float pdv[8], dsv[8];
 #pragma unroll
-            for (int h8 = 0; h8 < 16; h8 += 8) {
-              if (c + h8 < NU * 8) {
-                float pdv[8], dsv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float pj = pv[c + h8 + e];
-                  const float pa = fabsf(pj);
-                  const float m = pj < 0.f ? 0.f : dscale;        // (exact zero probabilities carry no sign: pd = 0 either way)
-                  pdv[e] = pa * m;
-                  rs += bf16_round(pdv[e]);
-                  dsv[e] = pa * (__uint_as_float(d16[h8 + e]) * m - delta) * p.scale;
-                }
-                const uint32_t off = unit_off(u0 + ((c + h8) >> 3));
-                *reinterpret_cast<uint4*>(pd_row + off) = make_uint4(pack_bf16(pdv[0], pdv[1]), pack_bf16(pdv[2], pdv[3]), pack_bf16(pdv[4], pdv[5]), pack_bf16(pdv[6], pdv[7]));
-                *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]), pack_bf16(dsv[4], dsv[5]), pack_bf16(dsv[6], dsv[7]));
+              for (int e = 0; e < 8; ++e) {
+                const float pj = pv[k * 8 + e];
+                const float pa = fabsf(pj);
+                const float m = pj < 0.f ? 0.f : dscale;        // (exact zero probabilities carry no sign: pd = 0 either way)
+                pdv[e] = pa * m;
+                dsv[e] = pa * (__uint_as_float(d8[e]) * m - delta) * p.scale;
               }
+              const uint32_t off = unit_off(u0 + u);
+              *reinterpret_cast<uint4*>(pd_row + off) = make_uint4(pack_bf16(pdv[0], pdv[1]), pack_bf16(pdv[2], pdv[3]), pack_bf16(pdv[4], pdv[5]), pack_bf16(pdv[6], pdv[7]));
+              *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]), pack_bf16(dsv[4], dsv[5]), pack_bf16(dsv[6], dsv[7]));
             }
           }
         }
-        if (valid) {
+        if (valid && part == 0) {
           // value-bias gradient through the dV MMA: Pd[row, sum_slot + 2 pi] = hi(rs), [.. + 1] = lo(rs); zeros for the other problems
-          const float hi = bf16_round(rs), lo = rs - hi;
+          const float rsum = (xch[512 + row] + xch[640 + row]) + (xch[768 + row] + xch[896 + row]);
+          const float hi = bf16_round(rsum), lo = rsum - hi;
           const uint32_t pair = pack_bf16(hi, lo);
           uint4 w = make_uint4(0, 0, 0, 0);
           if (rm.pi == 0) w.x = pair; else if (rm.pi == 1) w.y = pair; else if (rm.pi == 2) w.z = pair; else w.w = pair;
@@ -801,8 +823,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 4 + kBwdSoftmaxWarps) {
     // ===================== accumulators -> global: dQ, dK, dV (+ bias gradients) =====================
+    // 32 columns at a time (the 768-thread CTA leaves 80 registers per thread)
     const int slot = warp & 3;
     const int row = slot * 32 + lane;
     const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
@@ -824,13 +847,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(acc_full, (uint32_t)i & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < 3; ++m) {
-        uint32_t acc[64];         // one accumulator at a time: dQ, dK, dV
-        const uint32_t col = m == 0 ? C_DQ : (m == 1 ? C_DK : C_DV);
-        tmem_ld_x32(tmem_base + lane_field + col, &acc[0]);
-        tmem_ld_x32(tmem_base + lane_field + col + 32, &acc[32]);
+      for (int mh = 0; mh < 6; ++mh) {
+        const int m = mh >> 1, hf = mh & 1;           // accumulator (dQ, dK, dV), 32-column half
+        uint32_t acc[32];
+        const uint32_t col = (m == 0 ? C_DQ : (m == 1 ? C_DK : C_DV)) + (uint32_t)hf * 32u;
+        tmem_ld_x32(tmem_base + lane_field + col, acc);
         tmem_ld_wait();
-        if (m == 2) {                                   // the last accumulator is in registers: the next tile's MMAs may overwrite them
+        if (mh == 5) {                                // the last piece is in registers: the next tile's MMAs may overwrite the accumulators
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty);
@@ -838,8 +861,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         __nv_bfloat16* dst = m == 0 ? gq : (m == 1 ? gk : gv);
         if (dst != nullptr) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(dst + c * 8) =
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(dst + hf * 32 + c * 8) =
                 make_uint4(pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1])), pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3])),
                            pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5])), pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7])));
         }
@@ -847,47 +870,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (m == 0) {
             // query-bias gradient: column sums of this warp's 32 dQ rows (rows of no problem are exactly zero) by a halving
             // butterfly; the remainder warp of the 3-problem layout stops after the 8-lane groups (one problem each)
-            float v[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(acc[j]);
             const bool h1 = lane & 1, h2 = lane & 2, h4 = lane & 4, h8 = lane & 8, h16 = lane & 16;
-            float w32[32], w16[16], w8[8];
+            float w16[16], w8[8], w4[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) w32[j] = (h1 ? v[32 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, h1 ? v[j] : v[32 + j], 1);
+            for (int j = 0; j < 16; ++j)
+              w16[j] = __uint_as_float(h1 ? acc[16 + j] : acc[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(h1 ? acc[j] : acc[16 + j]), 1);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w16[j] = (h2 ? w32[16 + j] : w32[j]) + __shfl_xor_sync(0xffffffffu, h2 ? w32[j] : w32[16 + j], 2);
+            for (int j = 0; j < 8; ++j) w8[j] = (h2 ? w16[8 + j] : w16[j]) + __shfl_xor_sync(0xffffffffu, h2 ? w16[j] : w16[8 + j], 2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w8[j] = (h4 ? w16[8 + j] : w16[j]) + __shfl_xor_sync(0xffffffffu, h4 ? w16[j] : w16[8 + j], 4);
-            // lane now holds 8 columns starting at c8, summed over its group of 8 rows
-            const int c8 = (h1 ? 32 : 0) + (h2 ? 16 : 0) + (h4 ? 8 : 0);
+            for (int j = 0; j < 4; ++j) w4[j] = (h4 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, h4 ? w8[j] : w8[4 + j], 4);
+            // lane now holds 4 columns starting at c4, summed over its group of 8 rows
+            const int c4 = hf * 32 + (h1 ? 16 : 0) + (h2 ? 8 : 0) + (h4 ? 4 : 0);
             if (MULTI && slot == 3) {
               const int pi = lane >> 3;
               if (pi < np) {
-                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c8;
+                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c4;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) atomicAdd(bd + j, w8[j]);
+                for (int j = 0; j < 4; ++j) atomicAdd(bd + j, w4[j]);
               }
             } else {
-              float w4[4], w2[2];
+              float w2[2];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) w4[j] = (h8 ? w8[4 + j] : w8[j]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[j] : w8[4 + j], 8);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) w2[j] = (h16 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, h16 ? w4[j] : w4[2 + j], 16);
+              for (int j = 0; j < 2; ++j) w2[j] = (h8 ? w4[2 + j] : w4[j]) + __shfl_xor_sync(0xffffffffu, h8 ? w4[j] : w4[2 + j], 8);
+              const float w1 = (h16 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h16 ? w2[0] : w2[1], 16);
               int pi;
               if (g.regime == 0 || g.regime == 1) pi = slot; else if (g.regime == 2) pi = slot >> 1; else pi = 0;
-              if (pi < np) {
-                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c8 + (h8 ? 4 : 0) + (h16 ? 2 : 0);
-                atomicAdd(bd, w2[0]);
-                atomicAdd(bd + 1, w2[1]);
-              }
+              if (pi < np) atomicAdd(p.dbq + ((p0 + pi) % heads) * 64 + c4 + (h8 ? 2 : 0) + (h16 ? 1 : 0), w1);
             }
           } else if (m == 2) {
             // value-bias gradient: the dV rows of the spare key slots hold sum_q rs_q dO[q,:] (hi and lo part)
             const int k = row - p.sum_slot;
             if (k >= 0 && k < 2 * np) {
-              float* bd = p.dbv + ((p0 + (k >> 1)) % heads) * 64;
+              float* bd = p.dbv + ((p0 + (k >> 1)) % heads) * 64 + hf * 32;
 #pragma unroll
-              for (int j = 0; j < 64; ++j) atomicAdd(bd + j, __uint_as_float(acc[j]));
+              for (int j = 0; j < 32; ++j) atomicAdd(bd + j, __uint_as_float(acc[j]));
             }
           }
         }
@@ -1039,7 +1055,7 @@ static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
   p.mask_floats = a.mask != nullptr ? (uint32_t)(g.nwin * NCH * 32) : 0u;
   // (a 64-key chunk of Pd read as MN-major A operand with M = 128 reaches one chunk past a 64-key tile: keep 2 chunks per tile)
   const uint32_t tile_bytes = (kch < 2 ? 2u : kch) * 16384u;
-  const uint32_t fixed = 2 * tile_bytes + 4u * p.mask_floats * 4u + 256u;
+  const uint32_t fixed = 2 * tile_bytes + (uint32_t)kBwdSoftmaxWarps * p.mask_floats * 4u + 4096u + 256u;
   int ns = (int)((232448u - 1024u - fixed) / p.stage_bytes);
   if (ns > 4) ns = 4;
   if (ns < 2) return 1;                                   // does not fit: the caller falls back to the legacy kernel
@@ -1048,7 +1064,8 @@ static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
   p.off_ds = p.off_pd + tile_bytes;
   p.off_end = p.off_ds + tile_bytes;
   p.off_mask = p.off_end;
-  p.off_bar = (p.off_mask + 4u * p.mask_floats * 4u + 15u) & ~15u;
+  p.off_xch = (p.off_mask + (uint32_t)kBwdSoftmaxWarps * p.mask_floats * 4u + 15u) & ~15u;
+  p.off_bar = p.off_xch + 4096u;
   p.sum_slot = g.P * g.W;
   const size_t smem = p.off_bar + 256;
   p.tx_q32 = 32 * 128; p.tx_q8 = 8 * 128; p.tx_kv = (uint32_t)g.W * 128u;
@@ -1073,7 +1090,7 @@ static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = g.ntiles < num_sms_cached() ? g.ntiles : num_sms_cached();
-  launch_pdl(kern, grid, kThreads, smem, st, tq, tqr, tdo, tdor, tk, tv, p);
+  launch_pdl(kern, grid, kBwdThreads, smem, st, tq, tqr, tdo, tdor, tk, tv, p);
   return check_launch("attn_bwd_tc_kernel");
 }
 

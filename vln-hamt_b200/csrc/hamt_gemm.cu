@@ -832,10 +832,13 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
       }
       const int tm = (a.M + (cpair ? 255 : 127)) / (cpair ? 256 : 128), tn = (a.N + cbn - 1) / cbn;
       const int slots = cpair ? sms / 2 : sms;
-      // cycles per 64-deep k-block of one tile: tensor floor 4 x (128 x BN / 256) per SM; single-CTA tiles are limited by the
-      // L2 -> SM operand traffic when the whole chip runs them (measured ~1.1 PF for 128x256, ~0.75 PF for 128x128)
-      const double t_kb = cpair ? 540.0 : (cbn == 256 ? 600.0 : 340.0);
-      const double t_epi = (cbn == 256 ? 2400.0 : 1300.0) * (a.out_f32 ? 1.6 : 1.0);
+      // cycles per 64-deep k-block of one tile and per-tile epilogue cost: least-squares fit of this model to the measured K sweep
+      // of all three tile modes (tools/gemm_sweep.py, profiles/r02_gemm_sweep_v1.txt; 90 points, M = 1024 ... 34560): the 128 x 128
+      // tile is bound by the shared-memory operand bandwidth (2 x 16 KB per 256 MMA cycles) and runs at ~0.9-1.1 PF, 128 x 256 at
+      // ~1.5 PF, the CTA pair at ~1.6 PF.  (The round-1 constants 340 / 600 / 540 under-estimated the 128 x 128 tile and sent the
+      // K = 768 text-side GEMMs to it: 23 us instead of 17 us for 5120 x 2304 x 768.)
+      const double t_kb = cpair ? 673.0 : (cbn == 256 ? 749.0 : 575.0);
+      const double t_epi = (cbn == 256 ? 2367.0 : 1427.0) * (a.out_f32 ? 1.6 : 1.0);
       const bool forced = a.out_mode == 2 && a.splits > 0;
       for (int s = forced ? a.splits : 1; s <= (forced ? a.splits : 32); s *= 2) {
         if (a.out_mode != 2 && s > 1) break;
@@ -844,7 +847,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
         const int units = tm * tn * ((p.kb_total + kbs - 1) / kbs);
         const int waves = (units + slots - 1) / slots;
         const double unit = kbs * t_kb > t_epi ? kbs * t_kb : t_epi;
-        const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0) + (cpair ? 1500.0 : 0.0);   // pair: cluster sync + remote hand-offs
+        const double cost = waves * unit + t_epi + (s > 1 ? 600.0 * waves : 0.0) + (cpair ? 1370.0 : 0.0);   // pair: cluster sync + remote hand-offs
         if (cost < best) { best = cost; best_bn = cbn; best_s = s; best_pair = cpair; }
       }
     }
