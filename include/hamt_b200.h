@@ -61,6 +61,25 @@ int hamt_gemm_set_wide_epilogue(int on);
  * z_out (may alias x, may be null) receives dropout(x)+res in bf16; mean/rstd fp32 [M] (may be null). */
 int hamt_ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
                 float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+/* Pre-LN variant for the end-to-end ViT stage (Block.forward, pretrain_src/model/vision_transformer.py:195-198:
+ * x = x + sublayer(norm(x))): z = dropout(x) + res32 is the NEW residual stream (written in fp32 to z32 and in bf16 to z_out for the
+ * backward), y = LayerNorm_next(z) the input of the next sublayer.  x may be null (z = res32: the first norm of the backbone). */
+int hamt_ln_fwd_prenorm(const void* x, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out, float* z32,
+                        float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p,
+                        void* stream);
+/* PatchEmbed (vision_transformer.py:201-223): Conv2d(C, E, kernel = stride = patch) == GEMM over non-overlapping patches.  images fp32
+ * [N, C, H, W] -> out bf16 [N * (H/patch) * (W/patch), C * patch * patch], columns ordered (channel, row, column) like the flattened
+ * conv weight [E, C, patch, patch]. */
+int hamt_patchify_bf16(const float* images, void* out, int N, int C, int H, int W, int patch, void* stream);
+/* VisionTransformer.forward_features head (vision_transformer.py:337-342): x = pos_drop(cat(cls_token, patch tokens) + pos_embed).
+ * t0 bf16 [N * (S - 1), Hd] (patch projection incl. bias), cls fp32 [Hd], pos fp32 [S, Hd] -> x32 fp32 / x16 bf16 [N * S, Hd]. */
+int hamt_vit_embed_fwd(const void* t0, const float* cls, const float* pos, float* x32, void* x16, int N, int S, int Hd,
+                       const unsigned long long* seed_ptr, unsigned int site, float p, void* stream);
+/* backward of the above: dfull = dx o dropout mask (bf16 [N * S, Hd]; its column sums over N are the pos_embed / cls_token
+ * gradients), dt0 = the patch-token rows of dfull (bf16 [N * (S - 1), Hd], operand of the patch-projection wgrad). */
+int hamt_vit_embed_bwd(const void* dx, void* dfull, void* dt0, int N, int S, int Hd, const unsigned long long* seed_ptr, unsigned int site,
+                       float p, void* stream);
+
 /* backward: dx (grad of x, dropout applied; null to skip), dres = dz + dres_in (null to skip); dgamma/dbeta/dbias
  * (column sums, fp32) are ACCUMULATED into; any may be null. */
 int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,

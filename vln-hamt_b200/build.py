@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhamt_b200.so")
-SOURCES = ["hamt_abi.cu", "hamt_gemm.cu", "hamt_ln.cu", "hamt_attn.cu", "hamt_attn_tc.cu", "hamt_embed.cu", "hamt_heads.cu", "hamt_optim.cu"]
+SOURCES = ["hamt_abi.cu", "hamt_gemm.cu", "hamt_ln.cu", "hamt_attn.cu", "hamt_attn_tc.cu", "hamt_embed.cu", "hamt_heads.cu", "hamt_optim.cu", "hamt_vit.cu"]
 HEADERS = ["hamt_common.cuh", "hamt_kernels.h", os.path.join("..", "..", "include", "hamt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -51,7 +51,23 @@ int hamt_gemm_set_auto_pair(int on) { gemm_set_auto_pair(on); return 0; }
 
 int hamt_ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
                 float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
-  return ln_fwd(x, res, res32, gamma, beta, y, y32, z_out, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+  return ln_fwd(x, res, res32, gamma, beta, y, y32, z_out, nullptr, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+}
+int hamt_ln_fwd_prenorm(const void* x, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out, float* z32,
+                        float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p,
+                        void* stream) {
+  return ln_fwd(x, nullptr, res32, gamma, beta, y, y32, z_out, z32, mean, rstd, M, H, eps, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+}
+int hamt_patchify_bf16(const float* images, void* out, int N, int C, int H, int W, int patch, void* stream) {
+  return patchify_bf16(images, out, N, C, H, W, patch, (cudaStream_t)stream);
+}
+int hamt_vit_embed_fwd(const void* t0, const float* cls, const float* pos, float* x32, void* x16, int N, int S, int H,
+                       const unsigned long long* seed_ptr, unsigned int site, float p, void* stream) {
+  return vit_embed_fwd(t0, cls, pos, x32, x16, N, S, H, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+}
+int hamt_vit_embed_bwd(const void* dx, void* dfull, void* dt0, int N, int S, int H, const unsigned long long* seed_ptr, unsigned int site,
+                       float p, void* stream) {
+  return vit_embed_bwd(dx, dfull, dt0, N, S, H, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
 }
 int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
                 float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site, float p,

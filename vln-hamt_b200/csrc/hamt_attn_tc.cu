@@ -515,6 +515,7 @@ struct BwdParams {
   int sum_slot;                                   // first of the 2 P spare key slots that carry the Pd row sums (hi, lo per problem)
   uint32_t off_mask, mask_floats;                 // per softmax warp
   uint32_t off_xch;                               // fp32 [2][4][128]: per-part partial delta / Pd row sums of the tile rows
+  uint32_t off_dbias;                             // fp32 [5][heads * 64]: per-CTA bias-gradient sums, 4 epilogue warps x query bias + value bias (0 = not used: global atomics)
   uint32_t off_bar;
   uint32_t tx_q32, tx_q8, tx_kv;
   float scale_log2, scale;
@@ -675,6 +676,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // (profiles/r02_attn_bwd_notes.txt); the row-wide quantities (delta, the Pd row sum) now cross the four warps once per tile
     // through shared memory and a 128-thread named barrier.
     constexpr int MU = (NU + 3) / 4;
+    constexpr bool KEEP_DP = false;             // keeping dP in registers for pass 2 measured SLOWER (155 -> 165 us, panorama shape): 80-register budget
     const int slot = warp & 3;
     const int part = (warp - 4) >> 2;
     const int ub = (part * NU) >> 2, ue = ((part + 1) * NU) >> 2;       // this thread's units of the key window
@@ -726,6 +728,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       };
       // ---- pass 1: probabilities (kept in registers; the sign bit marks a dropped entry), partial delta and partial Pd row sum
       float pv[MU * 8];
+      uint32_t dpk[KEEP_DP ? MU * 8 : 1];        // dP of the thread's units, kept for pass 2 where the register budget allows
       float delta = 0.f, rs = 0.f;
       const uint32_t rowkey = attn_drop_rowkey(ds, (unsigned long long)pr * g.Sq + rm.qrow);
       const float* mrow = smask + (multi ? rm.pi * NCH * 32 : 0);
@@ -739,6 +742,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           load8(t_s, c, s8);
           load8(t_dp, c, d8);
           tmem_ld_wait();
+          if constexpr (KEEP_DP) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dpk[k * 8 + j] = d8[j];
+          }
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
             float ta, tb;
@@ -790,8 +797,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const int u = ub + k;
           if (u < ue) {
             uint32_t d8[8];
-            load8(t_dp, u * 8, d8);
-            tmem_ld_wait();
+            if constexpr (KEEP_DP) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d8[j] = dpk[k * 8 + j];
+            } else {
+              load8(t_dp, u * 8, d8);
+              tmem_ld_wait();
+            }
             if (valid) {
               float pdv[8], dsv[8];
 #pragma unroll
@@ -829,6 +841,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int slot = warp & 3;
     const int row = slot * 32 + lane;
     const uint32_t lane_field = (uint32_t)(slot * 32) << 16;
+    // Bias-gradient column sums are collected per CTA in shared memory and leave with ONE global atomic per column and CTA at the
+    // end.  Per-tile global atomics put ~10^6 adds on 1536 addresses for the panorama shape (155 us without, 250 us with bias
+    // gradients); shared-memory fp32 atomics are compare-and-swap loops on sm_100 and were worse still (433 us).  So there are NO
+    // atomics per tile: every epilogue warp owns a private [heads * 64] query-bias array (after the butterfly its lanes hold
+    // distinct columns; the problems of one tile have distinct heads), the value-bias array is only touched by the warp that
+    // holds the spare key rows.  Plain read-modify-write.
+    const int ew = warp - 4 - kBwdSoftmaxWarps;
+    float* sdbq = reinterpret_cast<float*>(smem_raw + p.off_dbias) + ew * heads * 64;
+    float* sdbv = reinterpret_cast<float*>(smem_raw + p.off_dbias) + 4 * heads * 64;
+    const bool cta_sums = p.dbq != nullptr && p.off_dbias != 0;
+    if (cta_sums) {
+      float* all = reinterpret_cast<float*>(smem_raw + p.off_dbias);
+      for (int j = ew * 32 + lane; j < 5 * heads * 64; j += 128) all[j] = 0.f;
+      asm volatile("bar.sync 6, 128;" ::: "memory");
+    }
     for (int i = 0; i < n_my; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int p0 = tile * g.P, np = min(g.P, g.nprob - p0);
@@ -884,9 +911,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (MULTI && slot == 3) {
               const int pi = lane >> 3;
               if (pi < np) {
-                float* bd = p.dbq + ((p0 + pi) % heads) * 64 + c4;
+                float* bd = (cta_sums ? sdbq : p.dbq) + ((p0 + pi) % heads) * 64 + c4;
+                if (cta_sums) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(bd + j, w4[j]);
+                  for (int j = 0; j < 4; ++j) bd[j] += w4[j];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) atomicAdd(bd + j, w4[j]);
+                }
               }
             } else {
               float w2[2];
@@ -895,18 +927,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               const float w1 = (h16 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h16 ? w2[0] : w2[1], 16);
               int pi;
               if (g.regime == 0 || g.regime == 1) pi = slot; else if (g.regime == 2) pi = slot >> 1; else pi = 0;
-              if (pi < np) atomicAdd(p.dbq + ((p0 + pi) % heads) * 64 + c4 + (h8 ? 2 : 0) + (h16 ? 1 : 0), w1);
+              if (pi < np) {
+                float* bd = (cta_sums ? sdbq : p.dbq) + ((p0 + pi) % heads) * 64 + c4 + (h8 ? 2 : 0) + (h16 ? 1 : 0);
+                if (cta_sums) *bd += w1; else atomicAdd(bd, w1);
+              }
             }
           } else if (m == 2) {
             // value-bias gradient: the dV rows of the spare key slots hold sum_q rs_q dO[q,:] (hi and lo part)
             const int k = row - p.sum_slot;
-            if (k >= 0 && k < 2 * np) {
+            const bool mine = k >= 0 && k < 2 * np;
+            if (cta_sums) {
+              // (the spare rows of one tile sit in ONE warp: sum_slot is a multiple of 8 and 2 P <= 8) hi + lo row of a problem are
+              // neighbouring lanes: fold them, then the even lane adds into the CTA's value-bias array
+              if (((p.sum_slot >> 5) & 3) == slot) {      // warp-uniform
+                float* bd = sdbv + ((p0 + (max(k, 0) >> 1)) % heads) * 64 + hf * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float v = __uint_as_float(acc[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(acc[j]), 1);
+                  if (mine && !(k & 1)) bd[j] += v;
+                }
+              }
+            } else if (mine) {
               float* bd = p.dbv + ((p0 + (k >> 1)) % heads) * 64 + hf * 32;
 #pragma unroll
               for (int j = 0; j < 32; ++j) atomicAdd(bd + j, __uint_as_float(acc[j]));
             }
           }
         }
+      }
+    }
+    if (cta_sums) {
+      asm volatile("bar.sync 6, 128;" ::: "memory");
+      const float* all = reinterpret_cast<const float*>(smem_raw + p.off_dbias);
+      const int hc = heads * 64;
+      for (int j = ew * 32 + lane; j < hc; j += 128) {
+        const float vq = (all[j] + all[hc + j]) + (all[2 * hc + j] + all[3 * hc + j]), vv = all[4 * hc + j];
+        if (vq != 0.f) atomicAdd(p.dbq + j, vq);
+        if (vv != 0.f) atomicAdd(p.dbv + j, vv);
       }
     }
   }
@@ -1055,7 +1112,9 @@ static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
   p.mask_floats = a.mask != nullptr ? (uint32_t)(g.nwin * NCH * 32) : 0u;
   // (a 64-key chunk of Pd read as MN-major A operand with M = 128 reaches one chunk past a 64-key tile: keep 2 chunks per tile)
   const uint32_t tile_bytes = (kch < 2 ? 2u : kch) * 16384u;
-  const uint32_t fixed = 2 * tile_bytes + (uint32_t)kBwdSoftmaxWarps * p.mask_floats * 4u + 4096u + 256u;
+  // (problems of one tile must have distinct heads: heads >= P; the spare key rows of a tile must sit in one warp: always true, see the kernel)
+  const uint32_t dbias_bytes = (b.dbq != nullptr && b.dbv != nullptr && a.heads <= 16 && a.heads >= g.P) ? (uint32_t)(5 * a.heads * 64 * 4) : 0u;
+  const uint32_t fixed = 2 * tile_bytes + (uint32_t)kBwdSoftmaxWarps * p.mask_floats * 4u + 4096u + dbias_bytes + 256u;
   int ns = (int)((232448u - 1024u - fixed) / p.stage_bytes);
   if (ns > 4) ns = 4;
   if (ns < 2) return 1;                                   // does not fit: the caller falls back to the legacy kernel
@@ -1065,7 +1124,8 @@ static int launch_bwd(const AttnBwdArgs& b, const Geom& g, cudaStream_t st) {
   p.off_end = p.off_ds + tile_bytes;
   p.off_mask = p.off_end;
   p.off_xch = (p.off_mask + (uint32_t)kBwdSoftmaxWarps * p.mask_floats * 4u + 15u) & ~15u;
-  p.off_bar = p.off_xch + 4096u;
+  p.off_dbias = dbias_bytes ? p.off_xch + 4096u : 0u;
+  p.off_bar = p.off_xch + 4096u + dbias_bytes;
   p.sum_slot = g.P * g.W;
   const size_t smem = p.off_bar + 256;
   p.tx_q32 = 32 * 128; p.tx_q8 = 8 * 128; p.tx_kv = (uint32_t)g.W * 128u;
@@ -1134,12 +1194,12 @@ int attn_bwd_tc(const AttnBwdArgs& b, cudaStream_t st, int* rc) {
   const AttnArgs& a = b.f;
   tc::Geom g;
   if (a.Sq > 128 || !tc::plan(g, a.B, a.heads, a.Sq, a.Sk, 128, 2) || g.QT != 1) return 0;     // + 2 spare key slots per problem (Pd row sums)
-  // Dispatch by measurement (profiles/r02_kbench_attn_bwd.txt, profiles/r02_attn_bwd_notes.txt): with one tile in flight per SM
-  // (TMEM holds S, dP and three accumulators of ONE tile; shared memory two 64 KB input stages next to 64 KB of Pd / dS) this
-  // kernel beats the legacy one where two ~53-row problems share a tile (53 x 53: 24.8 vs 30.2 us) and for short key axes
-  // (80 x 16: 21.2 vs 26.9 us), and loses on the panorama shape (279 vs 215 us) and on 80-key problems (41 vs 33-38 us).
+  // Dispatch by measurement (profiles/r02_kbench_attn_bwd_v6.txt, with fused bias gradients, us tcgen05 / legacy): panorama 36 x 36
+  // 174 / 216 (3 problems per tile), 53 x 53 23.9 / 30.1 (2 per tile), 80 x 80 36.5 / 37.5, 80 x 53 31.8 / 33.4 -- and it loses where a
+  // tile is mostly padding: 53 x 80 35.5 / 32.4 (one 53-row problem per 128-row tile, 2 x 80 keys exceed the 128-key accumulator),
+  // 16 x 80 33.8 / 19.9, 80 x 16 28.4 / 26.7, 16 x 16 14.7 / 8.8.
   if (tc::g_attn_impl != 2) {
-    const bool wins = (g.regime == 2 && g.P == 2) || (g.regime == 3 && g.W <= 16);
+    const bool wins = g.regime == 1 || (g.regime == 2 && g.P == 2) || (g.regime == 3 && a.Sq > 64 && g.W >= 48);
     if (!wins) return 0;
   }
   const int nu = g.W / 8;

@@ -28,8 +28,9 @@ struct DropArgs { const unsigned long long* seed_ptr; unsigned int site; float p
 
 // y = LN(drop(x) + res) * gamma + beta ; optionally stores z = drop(x)+res (bf16; may alias x) and row stats
 // res32 (fp32, instead of res) / y32 (fp32 copy of y): the full-precision residual stream, either may be null
+// z32 (fp32, may be null): the un-normalised sum as well -- the residual stream of PRE-LN blocks (ViT); x may be null (z = res32).
 int ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
-           float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st);
+           float* z32, float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st);
 // backward of the above.  dx = grad wrt x (dropout applied), dres = grad wrt res (+ dres_in), column sums accumulated
 // atomically into dgamma/dbeta/dbias (fp32, may be null).
 int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx,
@@ -94,6 +95,11 @@ struct EmbedFeatBwdArgs {
   float* db_lin;                  // bias grad of the image linear (column sum of dt) or null
 };
 int embed_feat_bwd(const EmbedFeatBwdArgs& a, cudaStream_t st);
+
+// end-to-end ViT stage (hamt_vit.cu)
+int patchify_bf16(const float* img, void* out, int N, int C, int Hh, int Ww, int ps, cudaStream_t st);   // fp32 NCHW -> bf16 [N*gh*gw, C*ps*ps]
+int vit_embed_fwd(const void* t0, const float* cls, const float* pos, float* x32, void* x16, int N, int S, int H, DropArgs drop, cudaStream_t st);
+int vit_embed_bwd(const void* dx, void* dfull, void* dt0, int N, int S, int H, DropArgs drop, cudaStream_t st);
 
 // misc bandwidth kernels
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);

@@ -55,7 +55,7 @@ template <int NCH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* may alias z_out */, const __nv_bfloat16* __restrict__ res,
                                                      const float* __restrict__ res32, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
-                                                     __nv_bfloat16* z_out, float* __restrict__ mean_out,
+                                                     __nv_bfloat16* z_out, float* __restrict__ z32, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int M, float eps, DropCfg dc) {
   pdl_grid_sync();
   constexpr int H = NCH * 256;
@@ -67,8 +67,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
   load_vec_f32<NCH>(beta, lane, b);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float z[NCH * 8];
-    load_row_bf16<NCH>(x + (long long)row * H, lane, z);
-    if (ds.on) {
+    if (x != nullptr) load_row_bf16<NCH>(x + (long long)row * H, lane, z);
+    else {                    // pre-LN entry: the row is the fp32 stream itself (res32)
+#pragma unroll
+      for (int i = 0; i < NCH * 8; ++i) z[i] = 0.f;
+    }
+    if (ds.on && x != nullptr) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -94,6 +98,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* x /* m
     for (int i = 0; i < NCH * 8; ++i) { const float d = z[i] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
     if (z_out != nullptr) store_row_bf16<NCH>(z_out + (long long)row * H, lane, z);
+    if (z32 != nullptr) {     // pre-LN blocks (ViT): the un-normalised sum IS the residual stream, carried in fp32
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float* p32 = z32 + (long long)row * H + c * 256 + lane * 8;
+        *reinterpret_cast<float4*>(p32) = make_float4(z[c * 8], z[c * 8 + 1], z[c * 8 + 2], z[c * 8 + 3]);
+        *reinterpret_cast<float4*>(p32 + 4) = make_float4(z[c * 8 + 4], z[c * 8 + 5], z[c * 8 + 6], z[c * 8 + 7]);
+      }
+    }
     float o[NCH * 8];
 #pragma unroll
     for (int i = 0; i < NCH * 8; ++i) o[i] = (z[i] - mean) * rstd * g[i] + b[i];
@@ -255,7 +267,9 @@ static int grid_for_rows(int M, int wpb, int max_ctas) {
 }
 
 int ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
-           float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st) {
+           float* z32, float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st) {
+  HAMT_REQUIRE(x != nullptr || res32 != nullptr, "ln_fwd: no input (x and res32 both null)");
+  HAMT_REQUIRE(((uintptr_t)z32 & 15) == 0 && (z32 == nullptr || z32 != res32 || x == nullptr || true), "ln_fwd: z32 must be 16-byte aligned");
   HAMT_REQUIRE(H == 512 || H == 768 || H == 1024, "ln_fwd: hidden size must be 512/768/1024");
   HAMT_REQUIRE(res == nullptr || res32 == nullptr, "ln_fwd: the residual comes either as bf16 or as fp32, not both");
   HAMT_REQUIRE((((uintptr_t)res32 | (uintptr_t)y32) & 15) == 0, "ln_fwd: fp32 residual / output must be 16-byte aligned");
@@ -263,9 +277,9 @@ int ln_fwd(const void* x, const void* res, const float* res32, const float* gamm
   DropCfg dc{drop.seed_ptr, drop.site, drop.p};
   const int grid = grid_for_rows(M, 8, 148 * 8);
   auto X = (const __nv_bfloat16*)x; auto R = (const __nv_bfloat16*)res; auto Y = (__nv_bfloat16*)y; auto Z = (__nv_bfloat16*)z_out;
-  if (H == 768) launch_pdl(ln_fwd_kernel<3>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
-  else if (H == 512) launch_pdl(ln_fwd_kernel<2>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
-  else launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, mean, rstd, M, eps, dc);
+  if (H == 768) launch_pdl(ln_fwd_kernel<3>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, z32, mean, rstd, M, eps, dc);
+  else if (H == 512) launch_pdl(ln_fwd_kernel<2>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, z32, mean, rstd, M, eps, dc);
+  else launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, X, R, res32, gamma, beta, Y, y32, Z, z32, mean, rstd, M, eps, dc);
   return check_launch("ln_fwd_kernel");
 }
 

@@ -569,8 +569,10 @@ class FeatEmbedFn(torch.autograd.Function):
             grads["dg_f"], grads["db_f"] = A.grad(P["ln_f"].weight), A.grad(P["ln_f"].bias)
         dt, dextra = ops.embed_feat_bwd(dy, t, ang, *ctx.base, grads, eps=run.eps, drop=ctx.d, want_dextra=ctx.has_extra, **ctx.kw)
         _wgrad(run, dt, x16, lin.weight)
+        # end-to-end stage: the features come from the ViT backbone and want their gradient (image_vilmodel.py:50-55)
+        dx16 = ops.gemm(dt, A.w16(lin.weight), b_mn=True) if ctx.needs_input_grad[4] else None
         ctx.saved = None
-        return (None, dextra) + (None,) * 8
+        return (None, dextra, None, None, dx16) + (None,) * 5
 
 
 class MeanPoolFn(torch.autograd.Function):
@@ -675,3 +677,127 @@ class GatherRowsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         return ops.scatter_rows(dy.to(BF16).contiguous(), ctx.idx, ctx.rows), None
+
+
+# ------------------------------------------------------------------------------------------------
+# end-to-end stage: ViT-B/16 backbone on the same kernels
+# ------------------------------------------------------------------------------------------------
+class CastFn(torch.autograd.Function):
+    """fp32 -> bf16 copy of the view features with a gradient (end-to-end stage: the features come out of the ViT)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.float()
+
+
+class VitFn(torch.autograd.Function):
+    """VisionTransformer.forward_features (pretrain_src/model/vision_transformer.py:335-348): images fp32 [N,3,H,W] -> class-token
+    features fp32 [N,E].
+
+    Pre-LN blocks (x = x + attn(norm1(x)); x = x + mlp(norm2(x)), :195-198) map onto the fused dropout + residual + LayerNorm kernel
+    shifted by one sublayer: the kernel that adds a sublayer's output to the fp32 residual stream also applies the NEXT sublayer's
+    LayerNorm (ops.ln_fwd_prenorm: z = drop(t) + x -> new stream in fp32, y = LN_next(z) in bf16), so a block is
+      qkv GEMM -> attention -> proj GEMM -> [add + norm2] -> fc1 GEMM (+GELU) -> fc2 GEMM -> [add + next norm1 / final norm]
+    with no stand-alone residual-add or LayerNorm pass.  The backward walks the sublayers in reverse with the same fused kernels
+    (ln_bwd adds the incoming stream gradient through its residual-gradient input)."""
+
+    @staticmethod
+    def forward(ctx, anchor, images, run: Run, vit):
+        A = run.arena
+        N = images.shape[0]
+        pe = vit.patch_embed
+        ps = pe.patch_size[0]
+        S, E, heads = pe.num_patches + 1, vit.embed_dim, vit.num_heads
+        eps = float(vit.norm.eps)            # 1e-6 (vision_transformer.py:265), not the BERT-side 1e-12 of an enclosing model's Run
+        patches = ops.patchify(images, ps)                                                         # [N*196, 3*16*16] bf16
+        w_pe = pe.proj.weight
+        t0 = ops.gemm(patches, A.w16(w_pe).view(E, -1), bias=pe.proj.bias)                          # Conv2d(k = s = 16) as a GEMM
+        d_pos = run.drop(vit.pos_drop)
+        x32, x16 = ops.vit_embed_fwd(t0, vit.cls_token.view(-1), vit.pos_embed.view(-1), N, S, d_pos)
+        blocks = list(vit.blocks)
+        n0 = blocks[0].norm1 if blocks else vit.norm
+        y, y32, _, _, mean0, rstd0 = ops.ln_fwd_prenorm(None, x32, n0.weight, n0.bias, eps, save=run.save, want_y32=not blocks)
+        saved = []
+        for i, blk in enumerate(blocks):
+            at, mlp = blk.attn, blk.mlp
+            qkv = ops.gemm(y, A.w16(at.qkv.weight), bias=at.qkv.bias)
+            d_att = run.drop(at.attn_drop)
+            c, lse = ops.attn_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], N, S, S, heads, None, d_att, need_lse=run.save)
+            t = ops.gemm(c, A.w16(at.proj.weight), bias=at.proj.bias)
+            d1 = run.drop(at.proj_drop)
+            y2, _, z1, x32, mean1, rstd1 = ops.ln_fwd_prenorm(t, x32, blk.norm2.weight, blk.norm2.bias, eps, d1, save=run.save)
+            d_mid = run.drop(mlp.drop)
+            h = torch.empty((N * S, mlp.fc1.weight.shape[0]), dtype=BF16, device=images.device) if run.save else None
+            a = ops.gemm(y2, A.w16(mlp.fc1.weight), bias=mlp.fc1.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE if run.save else ops.AUX_NONE, aux=h)
+            m_mid = None
+            if d_mid.p > 0:        # Mlp.drop between GELU and fc2 (:148): mask from the device hash, applied as an elementwise pass
+                m_mid = _post_drop_mask(a.view(-1, E), d_mid).view_as(a)
+                a = a * m_mid
+            t2 = ops.gemm(a, A.w16(mlp.fc2.weight), bias=mlp.fc2.bias)
+            d2 = run.drop(mlp.drop)
+            last = i + 1 == len(blocks)
+            nn_ = vit.norm if last else blocks[i + 1].norm1
+            yn, y32, z2, x32, mean2, rstd2 = ops.ln_fwd_prenorm(t2, x32, nn_.weight, nn_.bias, eps, d2, save=run.save, want_z32=not last, want_y32=last)
+            if run.save:
+                saved.append((y, qkv, c, lse, d_att, z1, mean1, rstd1, d1, y2, h, a, m_mid, z2, mean2, rstd2, d2))
+            y = yn
+        feats = y32.view(N, S, E)[:, 0].contiguous()                                                # fp32 class token after the final norm
+        ctx.run, ctx.vit, ctx.N, ctx.S = run, vit, N, S
+        ctx.saved = (patches, x16, mean0, rstd0, d_pos, saved) if run.save else None
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        run, vit, N, S = ctx.run, ctx.vit, ctx.N, ctx.S
+        A = run.arena
+        patches, x16, mean0, rstd0, d_pos, saved = ctx.saved
+        E, heads = vit.embed_dim, vit.num_heads
+        blocks = list(vit.blocks)
+        g_y = torch.zeros((N, S, E), dtype=BF16, device=dfeat.device)          # only the class token carries gradient out of the final norm
+        g_y[:, 0] = dfeat.to(BF16)
+        g_y = g_y.view(N * S, E)
+        g_x = None                                                            # gradient wrt the residual stream behind the current point
+        for i in range(len(blocks) - 1, -1, -1):
+            blk = blocks[i]
+            at, mlp = blk.attn, blk.mlp
+            y, qkv, c, lse, d_att, z1, mean1, rstd1, d1, y2, h, a, m_mid, z2, mean2, rstd2, d2 = saved[i]
+            nn_ = vit.norm if i + 1 == len(blocks) else blocks[i + 1].norm1
+            # ---- mlp sublayer (+ the LayerNorm that followed it)
+            dt2, g_x = ops.ln_bwd(g_y, z2, mean2, rstd2, nn_.weight, A.grad(nn_.weight), A.grad(nn_.bias), A.grad(mlp.fc2.bias), dres_in=g_x, drop=d2)
+            _wgrad(run, dt2, a, mlp.fc2.weight)
+            if m_mid is None:
+                dh = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=A.grad(mlp.fc1.bias))
+            else:
+                da = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True)
+                dh = _mul_dact(da * m_mid, h, ops.AUX_MUL_DGELU)
+                ops.colsum(dh, A.grad(mlp.fc1.bias))
+            _wgrad(run, dh, y2, mlp.fc1.weight)
+            g_y = ops.gemm(dh, A.w16(mlp.fc1.weight), b_mn=True)
+            # ---- attention sublayer (+ norm2)
+            dt, g_x = ops.ln_bwd(g_y, z1, mean1, rstd1, blk.norm2.weight, A.grad(blk.norm2.weight), A.grad(blk.norm2.bias), A.grad(at.proj.bias),
+                                 dres_in=g_x, drop=d1)
+            _wgrad(run, dt, c, at.proj.weight)
+            dc = ops.gemm(dt, A.w16(at.proj.weight), b_mn=True)
+            dqkv = torch.empty_like(qkv)
+            ops.attn_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], N, S, S, heads, None,
+                         d_att, dbias=A.grad(at.qkv.bias))
+            _wgrad(run, dqkv, y, at.qkv.weight)
+            g_y = ops.gemm(dqkv, A.w16(at.qkv.weight), b_mn=True)
+            saved[i] = None
+        n0 = blocks[0].norm1 if blocks else vit.norm
+        _, g_x = ops.ln_bwd(g_y, x16, mean0, rstd0, n0.weight, A.grad(n0.weight), A.grad(n0.bias), None, dres_in=g_x, want_dx=False)
+        dfull, dt0 = ops.vit_embed_bwd(g_x, N, S, d_pos)
+        col = torch.zeros(S * E, dtype=F32, device=dfeat.device)
+        ops.colsum(dfull.view(N, S * E), col)                                  # sum over the images: d pos_embed; its first row is d cls_token too
+        A.grad(vit.pos_embed).view(-1).add_(col)
+        A.grad(vit.cls_token).view(-1).add_(col[:E])
+        pe = vit.patch_embed
+        g_w = A.grad(pe.proj.weight).view(E, -1)
+        run.fork_wgrad(lambda: ops.gemm(dt0, patches, a_mn=True, b_mn=True, out=g_w, accumulate=True), dt0, patches)
+        ops.colsum(dt0, A.grad(pe.proj.bias))
+        ctx.saved = None
+        return None, None, None, None

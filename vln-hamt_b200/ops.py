@@ -318,3 +318,54 @@ def gather_rows_pad(table: torch.Tensor, idx: torch.Tensor, out: Optional[torch.
         raise ValueError("gather_rows_pad: out must be contiguous bf16 with n * H elements")
     _lib.check(_lib.load().hamt_gather_rows_pad_bf16(table.data_ptr(), table.shape[0], idx.data_ptr(), out.data_ptr(), n, H, _stream()), "gather_rows_pad")
     return out
+
+
+# ---- end-to-end ViT stage ------------------------------------------------------------------------------------------
+def ln_fwd_prenorm(x, res32, gamma, beta, eps: float, drop: Drop = NO_DROP, save: bool = True, want_z32: bool = True, want_y32: bool = False):
+    """Pre-LN residual step: z = dropout(x) + res32 (the new fp32 residual stream), y = LN(z).  x (bf16 [M,H]) may be None (z = res32).
+    Returns (y bf16, y32 or None, z16 (aliases x; None when x is None or not saved), z32 or None, mean, rstd)."""
+    M, H = res32.shape
+    if res32.dtype != F32 or not res32.is_contiguous() or (x is not None and (x.shape != res32.shape or not x.is_contiguous())):
+        raise ValueError("ln_fwd_prenorm: res32 must be contiguous fp32 [M, H] and x a contiguous bf16 tensor of the same shape")
+    y = torch.empty((M, H), dtype=BF16, device=res32.device)
+    y32 = torch.empty((M, H), dtype=F32, device=res32.device) if want_y32 else None
+    z32 = torch.empty((M, H), dtype=F32, device=res32.device) if (want_z32 and x is not None) else None
+    z16 = x if (save and x is not None) else None
+    mean = torch.empty(M, dtype=F32, device=res32.device) if save else None
+    rstd = torch.empty(M, dtype=F32, device=res32.device) if save else None
+    sp, site, p = drop.args
+    rc = _lib.load().hamt_ln_fwd_prenorm(_ptr(x), res32.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(y32), _ptr(z16), _ptr(z32),
+                                         _ptr(mean), _ptr(rstd), M, H, eps, sp, site, p, _stream())
+    _lib.check(rc, "ln_fwd_prenorm")
+    return y, y32, z16, z32, mean, rstd
+
+
+def patchify(images: torch.Tensor, patch: int) -> torch.Tensor:
+    """fp32 [N, C, H, W] -> bf16 [N * (H/patch) * (W/patch), C * patch * patch] (columns = channel, row, column)."""
+    if images.dtype != F32 or images.dim() != 4 or not images.is_contiguous() or not images.is_cuda:
+        raise ValueError("patchify: expected a contiguous CUDA fp32 [N, C, H, W] tensor")
+    N, C, Hh, Ww = images.shape
+    out = torch.empty((N * (Hh // patch) * (Ww // patch), C * patch * patch), dtype=BF16, device=images.device)
+    _lib.check(_lib.load().hamt_patchify_bf16(images.data_ptr(), out.data_ptr(), N, C, Hh, Ww, patch, _stream()), "patchify_bf16")
+    return out
+
+
+def vit_embed_fwd(t0: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, N: int, S: int, drop: Drop = NO_DROP):
+    """x = pos_drop(cat(cls, tokens) + pos): t0 bf16 [N*(S-1), H], cls fp32 [H], pos fp32 [S*H] -> (x32 fp32, x16 bf16) [N*S, H]."""
+    H = t0.shape[1]
+    x32 = torch.empty((N * S, H), dtype=F32, device=t0.device)
+    x16 = torch.empty((N * S, H), dtype=BF16, device=t0.device)
+    sp, site, p = drop.args
+    rc = _lib.load().hamt_vit_embed_fwd(t0.data_ptr(), cls.data_ptr(), pos.data_ptr(), x32.data_ptr(), x16.data_ptr(), N, S, H, sp, site, p, _stream())
+    _lib.check(rc, "vit_embed_fwd")
+    return x32, x16
+
+
+def vit_embed_bwd(dx: torch.Tensor, N: int, S: int, drop: Drop = NO_DROP):
+    """-> (dfull bf16 [N*S, H] = dx o mask, dt0 bf16 [N*(S-1), H] = its patch-token rows)."""
+    H = dx.shape[1]
+    dfull = torch.empty_like(dx)
+    dt0 = torch.empty((N * (S - 1), H), dtype=BF16, device=dx.device)
+    sp, site, p = drop.args
+    _lib.check(_lib.load().hamt_vit_embed_bwd(dx.data_ptr(), dfull.data_ptr(), dt0.data_ptr(), N, S, H, sp, site, p, _stream()), "vit_embed_bwd")
+    return dfull, dt0

@@ -146,3 +146,30 @@ def seeded_state_dict(model: torch.nn.Module, seed: int = 0, std: float = 0.02, 
             t = std * torch.randn(shape, generator=g)
         sd[k] = t.to(v.dtype)
     return sd
+
+
+def seeded_vit_state_dict(model: torch.nn.Module, seed: int = 0, std: float = 0.02):
+    """Deterministic initialisation of a ViT backbone's state_dict in key order (timm key names: `norm1` / `norm2` / `norm` are the
+    LayerNorms): weights ~ N(0, std), LayerNorm gamma = 1 + 0.1 N(0,1), every bias / beta / cls / pos ~ 0.02 N(0,1), so that no code
+    path is exercised at a trivial value.  Used for the reference class, the oracle and the CUDA module alike."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        shape = tuple(v.shape)
+        leaf = k.split(".")[-2] if "." in k else k
+        is_ln = leaf in ("norm", "norm1", "norm2")
+        if is_ln and k.endswith("weight"):
+            t = torch.ones(shape) + 0.1 * torch.randn(shape, generator=g)
+        elif k.endswith("bias") or k in ("cls_token", "pos_embed"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            t = std * torch.randn(shape, generator=g)
+        sd[k] = t.to(v.dtype)
+    return sd
+
+
+def make_images(n: int, seed: int = 0, size: int = 224) -> torch.Tensor:
+    """Synthetic normalised RGB views, fp32 [n, 3, size, size]: smooth low-frequency content + noise (ImageNet-normalised pixels are O(1))."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.nn.functional.interpolate(torch.randn(n, 3, 14, 14, generator=g), size=(size, size), mode="bilinear", align_corners=False)
+    return (low + 0.3 * torch.randn(n, 3, size, size, generator=g)).contiguous()

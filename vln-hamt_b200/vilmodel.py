@@ -349,6 +349,8 @@ def _additive_mask(mask: torch.Tensor) -> torch.Tensor:
 def _feat16(x: torch.Tensor) -> torch.Tensor:
     """Precomputed view features arrive as fp32 (collate) or bf16 (device-resident feature store): one cast kernel."""
     x = x.reshape(-1, x.shape[-1])
+    if x.dtype != BF16 and x.requires_grad:        # end-to-end stage: features computed by the ViT backbone inside this step
+        return Fn.CastFn.apply(x.float().contiguous())
     return ops.cast_bf16(x) if x.dtype != BF16 else x.contiguous()
 
 
