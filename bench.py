@@ -211,6 +211,91 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+VIT_FWD_GFLOP_PER_IMAGE = 35.1        # 12 blocks x (197 x (8 H^2 + 4 H I) + 4 x 197^2 x H) + the patch projection, H = 768, I = 3072
+
+
+def run_e2e_config(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: end-to-end stage (main_r2r_image.py / pretrain_r2r_e2e.json), the ViT-B/16 backbone trained jointly with
+    the cross-modal transformer from raw 224 x 224 views.  Per sample and step: T history views + 36 candidate views through the
+    backbone WITH gradient, T x 36 panorama views without (image_vilmodel.py:40-59).  Device-resident synthetic images (a batch is
+    gigabytes of fp32 pixels; the reference reads JPEGs from LMDB in its dataloader, out of scope), eager launches, fwd + bwd."""
+    import torch.distributed as dist
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import _lib, dp, synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.image_pretrain import MultiStepNavImagePreTraining
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, L = (args.batch if args.batch != 64 else 2), 5, 60            # pretrain_r2r_e2e.json: train_batch_size 1, max_txt_len 60
+    schedule = args.tasks.split(",") if args.tasks else SCHEDULE
+    model = MultiStepNavImagePreTraining(HamtConfig())
+    sd = synth.seeded_state_dict(model, seed=0, perturb_ln=False)
+    sd.update({"bert.vision_backbone." + k: v for k, v in synth.seeded_vit_state_dict(model.bert.vision_backbone, 1).items()})
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    arena = model.arena()
+    arena.ensure()
+    uniq = sorted(set(schedule))
+    batches = {t: synth.make_image_batch(t, batch_size=(B // 2 if t == "itm" and B > 1 else B), txt_len=L, hist_len=T, seed=7 + rank, device=str(dev)) for t in uniq}
+    n_img = {t: sum(int(np.prod(v.shape[:-3])) for k, v in batches[t].items() if k.endswith("images")) for t in uniq}
+    n_img_grad = {t: sum(int(np.prod(v.shape[:-3])) for k, v in batches[t].items() if k in ("hist_images", "ob_images")) for t in uniq}
+
+    def step(i):
+        t = schedule[i % len(schedule)]
+        np.random.seed(i); torch.manual_seed(i)
+        loss = model(batches[t], t, compute_loss=True)
+        loss.mean().backward()
+        if world > 1:
+            dp.sync_grads(arena)
+        model.zero_grad(set_to_none=True)
+        return batches[t]["txt_ids"].shape[0], n_img[t], n_img_grad[t]
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ns = ni = ng = 0
+    for i in range(args.steps):
+        a, b_, c = step(i)
+        ns += a; ni += b_; ng += c
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    clocks = sampler.result()
+    if rank == 0:
+        peaks = load_peaks()
+        vit_tf = VIT_FWD_GFLOP_PER_IMAGE * 1e9 * ((ni - ng) + 3 * ng) * world / (ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "pretrain samples/sec (fwd+bwd, R2R 6-task END-TO-END: ViT-B/16 on raw 224x224 views)", "value": round(ns * world / (ms * 1e-3), 2),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"R2R end-to-end pretrain (BASELINE configs[2]; pretrain_r2r_e2e.json), per sample {T} history views + 36 candidate views "
+                                   f"through ViT-B/16 with gradient, {T} x 36 panorama views without; txt{L}/hist{T}x36/obs37, 6-task schedule",
+                       "per_gpu_batch": B, "itm_batch": max(1, B // 2), "global_batch": B * world, "parallelism": f"dp{world}", "mode": "train (dropout 0.1)",
+                       "launch": "eager", "l2": "activations of a step (GBs) >> 126 MB L2"},
+            "images_per_s": round(ni * world / (ms * 1e-3), 1), "images_with_grad_per_s": round(ng * world / (ms * 1e-3), 1),
+            "vit_tflops": round(vit_tf, 1), "vit_frac_of_burst_peak": round(vit_tf / peaks["tf_burst"] / world, 3),
+            "gpu_launches": int(_lib.launch_count() - l0), "clocks": clocks,
+            "e2e": None, "e2e_note": "device-resident images only: the reference's stage-2 dataloader decodes LMDB JPEGs on the host (out of scope, SURVEY row 10); "
+                                     "a host leg would time PCIe, not this path"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,7 +303,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--config", default="r2r", choices=sorted(CONFIGS), help="BASELINE.json config: r2r = configs[1] (headline), rxr = configs[3], r4r = configs[4]")
+    ap.add_argument("--config", default="r2r", choices=sorted(CONFIGS) + ["e2e"],
+                    help="BASELINE.json config: r2r = configs[1] (headline), e2e = configs[2] (ViT-B/16 end-to-end stage), rxr = configs[3], r4r = configs[4]")
     ap.add_argument("--tasks", default=None, help="comma list overriding the 6-task schedule (e.g. sap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="--impl reference: skip the informational torch-eager-on-GPU timing of the oracle port")
@@ -242,7 +328,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.config == "e2e":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference's end-to-end stage does not import as shipped (image_pretrain.py:11, SURVEY row 10)"}))
+            return
         run_reference(args, rank)
+        return
+    if args.config == "e2e":
+        run_e2e_config(args, rank, world, local_rank)
         return
     if args.warmup < 3:
         args.warmup = 3

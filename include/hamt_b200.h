@@ -67,6 +67,12 @@ int hamt_ln_fwd(const void* x, const void* res, const float* res32, const float*
 int hamt_ln_fwd_prenorm(const void* x, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out, float* z32,
                         float* mean, float* rstd, int M, int H, float eps, const unsigned long long* seed_ptr, unsigned int site, float p,
                         void* stream);
+/* backward of hamt_ln_fwd_prenorm: like hamt_ln_bwd, but z is the residual STREAM (it is consumed again by every later sublayer), so the
+ * gradient of the sublayer output is the total gradient of z: dx = dropout-mask o (dz_LayerNorm + dres_in), dres = dz_LayerNorm + dres_in
+ * (dres is required; dres_in null = no later consumer: the last sublayer). */
+int hamt_ln_bwd_prenorm(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx,
+                        void* dres, float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site,
+                        float p, void* stream);
 /* PatchEmbed (vision_transformer.py:201-223): Conv2d(C, E, kernel = stride = patch) == GEMM over non-overlapping patches.  images fp32
  * [N, C, H, W] -> out bf16 [N * (H/patch) * (W/patch), C * patch * patch], columns ordered (channel, row, column) like the flattened
  * conv weight [E, C, patch, patch]. */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hamt_attn_set_impl": [i32],
     "hamt_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
     "hamt_ln_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, u32, f32, vp],
+    "hamt_ln_bwd_prenorm": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, u32, f32, vp],
     "hamt_ln_fwd_prenorm": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, f32, vp],
     "hamt_patchify_bf16": [vp, vp, i32, i32, i32, i32, i32, vp],
     "hamt_vit_embed_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp, u32, f32, vp],

@@ -72,7 +72,12 @@ int hamt_vit_embed_bwd(const void* dx, void* dfull, void* dt0, int N, int S, int
 int hamt_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
                 float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site, float p,
                 void* stream) {
-  return ln_bwd(dy, z, mean, rstd, gamma, dres_in, dx, dres, dgamma, dbeta, dbias, M, H, DropArgs{seed_ptr, site, p}, (cudaStream_t)stream);
+  return ln_bwd(dy, z, mean, rstd, gamma, dres_in, dx, dres, dgamma, dbeta, dbias, M, H, DropArgs{seed_ptr, site, p}, 0, (cudaStream_t)stream);
+}
+int hamt_ln_bwd_prenorm(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx,
+                        void* dres, float* dgamma, float* dbeta, float* dbias, int M, int H, const unsigned long long* seed_ptr, unsigned int site,
+                        float p, void* stream) {
+  return ln_bwd(dy, z, mean, rstd, gamma, dres_in, dx, dres, dgamma, dbeta, dbias, M, H, DropArgs{seed_ptr, site, p}, 1, (cudaStream_t)stream);
 }
 
 int hamt_attn_fwd(const void* q, const void* k, const void* v, long long q_bstride, long long kv_bstride, long long ldq, long long ldkv,

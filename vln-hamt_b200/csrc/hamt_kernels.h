@@ -33,8 +33,9 @@ int ln_fwd(const void* x, const void* res, const float* res32, const float* gamm
            float* z32, float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st);
 // backward of the above.  dx = grad wrt x (dropout applied), dres = grad wrt res (+ dres_in), column sums accumulated
 // atomically into dgamma/dbeta/dbias (fp32, may be null).
+// prenorm = 1 (ViT blocks): z is the residual stream itself, so dx = dropout-mask o (dz + dres_in) instead of dropout-mask o dz.
 int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx,
-           void* dres, float* dgamma, float* dbeta, float* dbias, int M, int H, DropArgs drop, cudaStream_t st);
+           void* dres, float* dgamma, float* dbeta, float* dbias, int M, int H, DropArgs drop, int prenorm, cudaStream_t st);
 
 struct AttnArgs {
   const void* q; const void* k; const void* v;       // bf16; element (b, s, h, d) at ptr + b*bstride + s*ld + h*64 + d

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                         const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres_in,
                                                         __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
-                                                        float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc) {
+                                                        float* dgamma, float* dbeta, float* dbias, int M, DropCfg dc, int prenorm) {
   pdl_grid_sync();
   constexpr int H = NCH * 256;
   constexpr int NV = NCH * 8;                          // values per lane
@@ -224,6 +224,12 @@ __global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const __nv_bfloat16* __r
           for (int j = 0; j < 8; ++j) o8[j] = dz[j];
         }
         *reinterpret_cast<uint4*>(dres + o + c * 256) = pack8(o8);
+        // pre-LN blocks: z is the residual STREAM (consumed again further down), so the sublayer output's gradient is the total
+        // gradient of z -- LayerNorm path + incoming stream gradient -- not the LayerNorm path alone
+        if (prenorm) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] = o8[j];
+        }
       }
       if (dx != nullptr) {
         if (ds.on) {
@@ -268,9 +274,9 @@ static int grid_for_rows(int M, int wpb, int max_ctas) {
 
 int ln_fwd(const void* x, const void* res, const float* res32, const float* gamma, const float* beta, void* y, float* y32, void* z_out,
            float* z32, float* mean, float* rstd, int M, int H, float eps, DropArgs drop, cudaStream_t st) {
-  HAMT_REQUIRE(x != nullptr || res32 != nullptr, "ln_fwd: no input (x and res32 both null)");
-  HAMT_REQUIRE(((uintptr_t)z32 & 15) == 0 && (z32 == nullptr || z32 != res32 || x == nullptr || true), "ln_fwd: z32 must be 16-byte aligned");
   HAMT_REQUIRE(H == 512 || H == 768 || H == 1024, "ln_fwd: hidden size must be 512/768/1024");
+  HAMT_REQUIRE(x != nullptr || res32 != nullptr, "ln_fwd: no input (x and res32 both null)");
+  HAMT_REQUIRE(((uintptr_t)z32 & 15) == 0, "ln_fwd: z32 must be 16-byte aligned");
   HAMT_REQUIRE(res == nullptr || res32 == nullptr, "ln_fwd: the residual comes either as bf16 or as fp32, not both");
   HAMT_REQUIRE((((uintptr_t)res32 | (uintptr_t)y32) & 15) == 0, "ln_fwd: fp32 residual / output must be 16-byte aligned");
   if (M <= 0) return 0;
@@ -284,7 +290,8 @@ int ln_fwd(const void* x, const void* res, const float* res32, const float* gamm
 }
 
 int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma, const void* dres_in, void* dx, void* dres,
-           float* dgamma, float* dbeta, float* dbias, int M, int H, DropArgs drop, cudaStream_t st) {
+           float* dgamma, float* dbeta, float* dbias, int M, int H, DropArgs drop, int prenorm, cudaStream_t st) {
+  HAMT_REQUIRE(!prenorm || dres != nullptr, "ln_bwd (pre-LN): the stream gradient output is required");
   HAMT_REQUIRE(H == 512 || H == 768 || H == 1024, "ln_bwd: hidden size must be 512/768/1024");
   HAMT_REQUIRE((((uintptr_t)dgamma | (uintptr_t)dbeta | (uintptr_t)dbias) & 15) == 0, "ln_bwd: column-sum outputs must be 16-byte aligned");
   if (M <= 0) return 0;
@@ -308,9 +315,9 @@ int ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, 
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -3; }
     attr_set = true;
   }
-  if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
-  else launch_pdl(ln_bwd_kernel<4>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc);
+  if (H == 768) launch_pdl(ln_bwd_kernel<3>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc, prenorm);
+  else if (H == 512) launch_pdl(ln_bwd_kernel<2>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc, prenorm);
+  else launch_pdl(ln_bwd_kernel<4>, grid, 256, smem, st, DY, Z, mean, rstd, gamma, DRI, DX, DR, dgamma, dbeta, dbias, M, dc, prenorm);
   return check_launch("ln_bwd_kernel");
 }
 

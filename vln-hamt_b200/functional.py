@@ -529,6 +529,7 @@ class TextEmbedFn(torch.autograd.Function):
                            emb.LayerNorm.weight, A.grad(emb.word_embeddings.weight), A.grad(emb.position_embeddings.weight),
                            A.grad(emb.token_type_embeddings.weight)[0], A.grad(emb.LayerNorm.weight), A.grad(emb.LayerNorm.bias), ctx.run.eps,
                            ctx.d)
+        ctx.run._hook(emb)          # data-parallel: the embedding tables' gradients (94 MB) are final -- exchange them now
         return None, None, None, None
 
 
@@ -767,7 +768,7 @@ class VitFn(torch.autograd.Function):
             y, qkv, c, lse, d_att, z1, mean1, rstd1, d1, y2, h, a, m_mid, z2, mean2, rstd2, d2 = saved[i]
             nn_ = vit.norm if i + 1 == len(blocks) else blocks[i + 1].norm1
             # ---- mlp sublayer (+ the LayerNorm that followed it)
-            dt2, g_x = ops.ln_bwd(g_y, z2, mean2, rstd2, nn_.weight, A.grad(nn_.weight), A.grad(nn_.bias), A.grad(mlp.fc2.bias), dres_in=g_x, drop=d2)
+            dt2, g_x = ops.ln_bwd(g_y, z2, mean2, rstd2, nn_.weight, A.grad(nn_.weight), A.grad(nn_.bias), A.grad(mlp.fc2.bias), dres_in=g_x, drop=d2, prenorm=True)
             _wgrad(run, dt2, a, mlp.fc2.weight)
             if m_mid is None:
                 dh = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=A.grad(mlp.fc1.bias))
@@ -779,7 +780,7 @@ class VitFn(torch.autograd.Function):
             g_y = ops.gemm(dh, A.w16(mlp.fc1.weight), b_mn=True)
             # ---- attention sublayer (+ norm2)
             dt, g_x = ops.ln_bwd(g_y, z1, mean1, rstd1, blk.norm2.weight, A.grad(blk.norm2.weight), A.grad(blk.norm2.bias), A.grad(at.proj.bias),
-                                 dres_in=g_x, drop=d1)
+                                 dres_in=g_x, drop=d1, prenorm=True)
             _wgrad(run, dt, c, at.proj.weight)
             dc = ops.gemm(dt, A.w16(at.proj.weight), b_mn=True)
             dqkv = torch.empty_like(qkv)

@@ -23,6 +23,13 @@ class NavImagePreTrainedModel(NavPreTrainedModel):
         self.vision_backbone = vit_base_patch16_224(drop_rate=config.hidden_dropout_prob, attn_drop_rate=config.attention_probs_dropout_prob,
                                                     drop_path_rate=0.0, depth=vit_depth)
         object.__setattr__(self.vision_backbone, "_arena_owner", self)
+        # registered first in the reference (:25): same state_dict key order
+        vb = self._modules.pop("vision_backbone")
+        rest = list(self._modules.items())
+        self._modules.clear()
+        self._modules["vision_backbone"] = vb
+        for k, v in rest:
+            self._modules[k] = v
 
     def forward_vision_backbone(self, images: torch.Tensor, detach: bool = False, _run=None) -> torch.Tensor:
         """image_vilmodel.py:40-59: [N,T,3,H,W] -> [N,T,768]; [N,T,P,3,H,W] (panorama views) -> [N,T,P,768] under no_grad."""

@@ -105,13 +105,15 @@ def ln_fwd(x, res, gamma, beta, eps: float, drop: Drop = NO_DROP, save_z: bool =
 
 
 def ln_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, dbias=None, dres_in=None, want_dx: bool = True, want_dres: bool = True, drop: Drop = NO_DROP,
-           dres_out=None):
-    """Returns (dx, dres); column sums are accumulated into dgamma / dbeta / dbias (fp32)."""
+           dres_out=None, prenorm: bool = False):
+    """Returns (dx, dres); column sums are accumulated into dgamma / dbeta / dbias (fp32).  prenorm (ViT blocks): z is the residual
+    stream, dx = mask o (dz + dres_in)."""
     M, H = dy.shape
     dx = torch.empty_like(dy) if want_dx else None
     dres = (torch.empty_like(dy) if dres_out is None else dres_out) if want_dres else None
     sp, site, p = drop.args
-    rc = _lib.load().hamt_ln_bwd(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _ptr(dres_in), _ptr(dx), _ptr(dres),
+    lib = _lib.load()
+    rc = (lib.hamt_ln_bwd_prenorm if prenorm else lib.hamt_ln_bwd)(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _ptr(dres_in), _ptr(dx), _ptr(dres),
                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias), M, H, sp, site, p, _stream())
     _lib.check(rc, "ln_bwd")
     return dx, dres

@@ -88,9 +88,12 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
     def __init__(self, config):
         super().__init__(config)
         self.config = config
-        self.bert = NavPreTrainedModel(config)
+        self.bert = self._make_backbone(config)
         self.bert._arena_owner = None
         object.__setattr__(self.bert, "_arena_owner", self)       # one arena for backbone + heads (not a submodule cycle)
+        vb = getattr(self.bert, "vision_backbone", None)          # end-to-end stage (image_pretrain.py): the ViT shares it too
+        if vb is not None:
+            object.__setattr__(vb, "_arena_owner", self)
         if 'mlm' in config.pretrain_tasks:
             self.mlm_head = BertOnlyMLMHead(self.config)
         if 'sap' in config.pretrain_tasks:
@@ -105,6 +108,9 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
             self.itm_head = ItmPrediction(self.config.hidden_size)
         self.init_weights()
         self.tie_weights()
+
+    def _make_backbone(self, config):
+        return NavPreTrainedModel(config)
 
     def tie_weights(self):
         if 'mlm' in self.config.pretrain_tasks:

@@ -173,3 +173,23 @@ def make_images(n: int, seed: int = 0, size: int = 224) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     low = torch.nn.functional.interpolate(torch.randn(n, 3, 14, 14, generator=g), size=(size, size), mode="bilinear", align_corners=False)
     return (low + 0.3 * torch.randn(n, 3, size, size, generator=g)).contiguous()
+
+
+def make_image_batch(task: str, batch_size: int = 1, txt_len: int = 60, hist_len: int = 5, n_pano: int = 36, n_ob: int = 37, seed: int = 0,
+                     size: int = 224, device: str = "cpu") -> Dict[str, Optional[torch.Tensor]]:
+    """End-to-end stage batch (image collate of the reference's stage 2: `hist_images` [B,T,3,S,S], `hist_pano_images`
+    [B,T,P,3,S,S], `ob_images` [B,O-1,3,S,S], `ob_v_exists`; image_pretrain.py:47-90 keys) on top of make_batch's text / angle / label
+    tensors.  Images are normalised fp32 pixels; they are drawn directly on `device` (seeded) because a batch is gigabytes."""
+    b = make_batch(task, batch_size=batch_size, txt_len=txt_len, hist_len=hist_len, n_pano=n_pano, n_ob=n_ob, feat=8, seed=seed)
+    for k in ("hist_img_fts", "hist_pano_img_fts", "ob_img_fts"):
+        b.pop(k, None)
+    out = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in b.items()}
+    g = torch.Generator(device=device).manual_seed(seed + 77)
+    B, T, P, O = batch_size, hist_len, n_pano, n_ob
+    if T > 0:
+        out["hist_images"] = torch.randn(B, T, 3, size, size, generator=g, device=device)
+        out["hist_pano_images"] = torch.randn(B, T, P, 3, size, size, generator=g, device=device)
+    if task in ("sap", "sar", "sprel"):
+        out["ob_images"] = torch.randn(B, O - 1, 3, size, size, generator=g, device=device)
+        out["ob_v_exists"] = torch.ones(B, O - 1, dtype=torch.bool, device=device)
+    return out
