@@ -242,17 +242,32 @@ def run_e2e_config(args, rank, world, local_rank):
     n_img = {t: sum(int(np.prod(v.shape[:-3])) for k, v in batches[t].items() if k.endswith("images")) for t in uniq}
     n_img_grad = {t: sum(int(np.prod(v.shape[:-3])) for k, v in batches[t].items() if k in ("hist_images", "ob_images")) for t in uniq}
 
+    use_graphs = not args.no_graphs
+    trainer = None
+    if use_graphs:
+        from hamt_b200 import graph
+        trainer = graph.GraphedTrainer(model, post_backward=(lambda: dp.sync_grads(arena)) if world > 1 else None)
+        for t in uniq:       # masked-row indices / the ITM negative plan are host-side parts of the batch (graph.py)
+            hb = dict(batches[t])
+            if t == "itm":
+                hb["_hist_masks_host"] = hb["hist_masks"].cpu()
+            np.random.seed(0); torch.manual_seed(0)
+            batches[t] = graph.add_sync_free_extras(t, hb, device=dev)
+
     def step(i):
         t = schedule[i % len(schedule)]
         np.random.seed(i); torch.manual_seed(i)
-        loss = model(batches[t], t, compute_loss=True)
-        loss.mean().backward()
-        if world > 1:
-            dp.sync_grads(arena)
-        model.zero_grad(set_to_none=True)
+        if trainer is not None:
+            trainer.step(t, batches[t])
+        else:
+            loss = model(batches[t], t, compute_loss=True)
+            loss.mean().backward()
+            if world > 1:
+                dp.sync_grads(arena)
+            model.zero_grad(set_to_none=True)
         return batches[t]["txt_ids"].shape[0], n_img[t], n_img_grad[t]
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3, len(schedule) if use_graphs else 0)):       # every task's graph is captured in warm-up
         step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -286,10 +301,11 @@ def run_e2e_config(args, rank, world, local_rank):
             "config": {"workload": f"R2R end-to-end pretrain (BASELINE configs[2]; pretrain_r2r_e2e.json), per sample {T} history views + 36 candidate views "
                                    f"through ViT-B/16 with gradient, {T} x 36 panorama views without; txt{L}/hist{T}x36/obs37, 6-task schedule",
                        "per_gpu_batch": B, "itm_batch": max(1, B // 2), "global_batch": B * world, "parallelism": f"dp{world}", "mode": "train (dropout 0.1)",
-                       "launch": "eager", "l2": "activations of a step (GBs) >> 126 MB L2"},
+                       "launch": "cuda-graph per task" if use_graphs else "eager", "l2": "activations of a step (GBs) >> 126 MB L2"},
             "images_per_s": round(ni * world / (ms * 1e-3), 1), "images_with_grad_per_s": round(ng * world / (ms * 1e-3), 1),
             "vit_tflops": round(vit_tf, 1), "vit_frac_of_burst_peak": round(vit_tf / peaks["tf_burst"] / world, 3),
-            "gpu_launches": int(_lib.launch_count() - l0), "clocks": clocks,
+            "gpu_launches": int(_lib.launch_count() - l0) if trainer is None else int(sum(trainer.steps[k].native_launches for k in trainer.steps) * args.steps / max(1, len(trainer.steps))),
+            "clocks": clocks,
             "e2e": None, "e2e_note": "device-resident images only: the reference's stage-2 dataloader decodes LMDB JPEGs on the host (out of scope, SURVEY row 10); "
                                      "a host leg would time PCIe, not this path"}), flush=True)
     if world > 1:

@@ -37,7 +37,9 @@ long long hamt_launch_count(void);
  *   wgrad    dW = dy^T x         : A = dy (a_mn 1), B = x (b_mn 1), fp32 out, out_mode 2
  * out_f32: 0 bf16 / 1 fp32 output.  out_mode: 0 store, 1 out += , 2 out += with split-K atomics.
  * act: 0 none, 1 exact-erf GELU (vilmodel.py:23-29), 2 ReLU (pretrain_cmt.py:16).
- * aux_mode: 0 none, 1 also store the pre-activation (bf16) to aux, 2 multiply by dGELU(aux), 3 by (aux > 0).
+ * aux_mode: 0 none, 1 also store the pre-activation (bf16) to aux, 2 multiply by dGELU(aux), 3 by (aux > 0),
+ *           4 (with act = gelu) store gelu'(pre-activation) to aux instead -- BertIntermediate forward, vilmodel.py:168-171 -- so that
+ *           5 multiply by aux is the whole BertOutput-dgrad epilogue (the erf-GELU derivative is evaluated once, in the forward).
  * tile_n: 0 auto / 128 / 256 (one CTA per 128 x tile_n tile) / 512 (CTA pair, 256 x 256 tile, tcgen05 cta_group::2).  splits: 0 auto.
  * colsum: fp32 [N] or null; the epilogue ACCUMULATES the column sums of the stored bf16 output into it -- the bias gradient of
  *   the Linear that produced the activation whose gradient this GEMM writes (replaces a separate pass over [M,N]); bf16 store only. */

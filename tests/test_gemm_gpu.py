@@ -89,6 +89,34 @@ def test_gemm_dgrad_dgelu_epilogue():
     assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("M,tile_n", [(384, 0), (5120, 0), (777, 128), (1024, 256), (1024, 512)])
+def test_gemm_gelu_derivative_store_and_multiply_epilogues(M, tile_n):
+    """Round-2 FFN pair: the forward epilogue stores gelu'(pre) next to gelu(pre) (aux_mode 4), the backward epilogue multiplies the
+    dgrad by that saved derivative (aux_mode 5) with the fused bias column sums -- against torch's erf GELU and its autograd."""
+    ops = _ops()
+    N, K = 3072, 768
+    a, b = _rand((M, K), 21), _rand((N, K), 22, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(23)).cuda() * 0.1
+    der = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU, aux=der, tile_n=tile_n)
+    pre = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    ref = torch.nn.functional.gelu(pre)
+    ref.sum().backward()
+    assert (out.float() - ref.detach()).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+    # the derivative is O(1) (range [-0.13, 1.13]); bf16 storage + the bf16-level uncertainty of pre itself
+    assert (der.float() - pre.grad).abs().max().item() <= 1.5e-2
+    # identical activation output as the pre-activation-saving epilogue
+    aux = torch.empty_like(der)
+    out1 = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=aux, tile_n=tile_n)
+    assert torch.equal(out, out1)
+    dy, w = _rand((M, K), 24), _rand((K, N), 25, 0.05)
+    cs = torch.zeros(N, dtype=torch.float32, device="cuda")
+    dh = ops.gemm(dy, w, b_mn=True, aux_mode=ops.AUX_MUL, aux=der, colsum=cs, tile_n=tile_n)
+    want = (dy.float() @ w.float()) * der.float()
+    assert (dh.float() - want).abs().max().item() <= 1e-2 * want.abs().max().item() + 1e-3
+    assert (cs - dh.float().sum(0)).abs().max().item() <= 2e-3 * dh.float().abs().sum(0).max().item() + 1e-3
+
+
 @pytest.mark.parametrize("Mred,N,K", [(5120, 768, 768), (3392, 3072, 768), (1000, 768, 3072), (160, 2304, 768), (34560, 768, 768)])
 def test_gemm_wgrad_mn_major_both_splitk(Mred, N, K):
     """dW[N,K] += dy[Mred,N]^T @ x[Mred,K]: both operands MN-major, fp32 output, split-K atomics."""

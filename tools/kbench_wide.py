@@ -20,6 +20,8 @@ for M in (34560, 5120):
     cases = {"store N=3072": lambda: ops.gemm(x, w1, bias=b1), "store N=768 K=3072": lambda: ops.gemm(dh, w2, bias=b1[:768].contiguous()),
              "gelu+pre": lambda: ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=h),
              "dgelu+colsum": lambda: ops.gemm(dt, w2, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=cs),
+             "gelu+derivative (r2)": lambda: ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU, aux=h),
+             "mul-aux+colsum (r2)": lambda: ops.gemm(dt, w2, b_mn=True, aux_mode=ops.AUX_MUL, aux=h, colsum=cs),
              "accum K=3072": lambda: ops.gemm(dh, w3, b_mn=True, out=dx, accumulate=True)}
     row = {"M": M}
     for name, fn in cases.items():
@@ -29,17 +31,3 @@ for M in (34560, 5120):
     lib.hamt_gemm_set_wide_epilogue(0)
     print(json.dumps(row), flush=True)
 
-# LayerNorm backward: default kernel vs the experimental variants (hamt_ln_set_variant)
-for M in (34560, 8512, 5120, 3392):
-    x = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
-    r = torch.randn(M, 768, device="cuda").to(torch.bfloat16)
-    gm, bt = torch.ones(768, device="cuda"), torch.zeros(768, device="cuda")
-    y, z, mean, rstd = ops.ln_fwd(x.clone(), r, gm, bt, 1e-12)
-    dy, dri = torch.randn(M, 768, device="cuda").to(torch.bfloat16), torch.randn(M, 768, device="cuda").to(torch.bfloat16)
-    dg, db, dbias = (torch.zeros(768, device="cuda") for _ in range(3))
-    row = {"ln_bwd_M": M}
-    for v in (0, 1, 2, 3):
-        lib.hamt_ln_set_variant(v)
-        row[f"variant{v}_us"] = round(timeit(lambda: ops.ln_bwd(dy, z, mean, rstd, gm, dg, db, dbias, dres_in=dri)) * 1e3, 1)
-    lib.hamt_ln_set_variant(0)
-    print(json.dumps(row), flush=True)

@@ -39,7 +39,8 @@ struct GemmParams {
   int out_mode;       // 0: store, 1: out += acc (plain RMW), 2: atomic add (split-K)
   const float* bias;  // [N] or null
   int act;            // 0 none, 1 gelu(erf), 2 relu
-  int aux_mode;       // 0 none, 1 store pre-activation (bf16) to aux, 2 multiply by dgelu(aux), 3 multiply by (aux > 0)
+  int aux_mode;       // 0 none, 1 store pre-activation (bf16) to aux, 2 multiply by dgelu(aux), 3 multiply by (aux > 0),
+                      // 4 store gelu'(pre-activation) to aux, 5 multiply by aux
   __nv_bfloat16* aux;
   long long ld_aux;
   float alpha;
@@ -79,8 +80,14 @@ enum : int {
   EPI_GELU_PRE = 2,   // bf16 store of gelu(acc + bias), pre-activation stored to aux        (BertIntermediate forward)
   EPI_DGELU = 3,      // bf16 store of acc * gelu'(aux) (+ fused column sums)                 (BertOutput dgrad)
   EPI_ACCUM = 4,      // bf16 out += acc                                                      (dgrad onto the residual-path gradient)
-  EPI_F32 = 5         // fp32 store / RMW / split-K red                                       (wgrad, logits)
+  EPI_F32 = 5,        // fp32 store / RMW / split-K red                                       (wgrad, logits)
+  EPI_GELU_DER = 6,   // bf16 store of gelu(acc + bias), gelu'(acc + bias) stored to aux      (BertIntermediate forward, round 2)
+  EPI_MULAUX = 7      // bf16 store of acc * aux (+ fused column sums)                        (BertOutput dgrad on the saved derivative)
 };
+// Round 2: the forward GELU epilogue can save the DERIVATIVE gelu'(pre) instead of the pre-activation (one more ex2 on the pass that
+// already evaluates the Gaussian tail), so the backward epilogue is a single multiply instead of 2 MUFU + ~20 ALU per element: the
+// dGELU dgrad was the most expensive GEMM signature of the step (profiles/r01_ncu_ffn_gemms_v6.txt: 272 us at M = 34 560 against
+// 117 us for the plain store; 183 us with the 16-warp epilogue).
 
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -404,10 +411,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int as = 0;
     uint32_t aphase = 0;
     const bool out_f32 = GEN ? (p.out_f32 != 0) : (EPI == EPI_F32);
-    const int act = GEN ? p.act : (EPI == EPI_GELU_PRE ? 1 : 0);
-    const int aux_mode = GEN ? p.aux_mode : (EPI == EPI_GELU_PRE ? 1 : (EPI == EPI_DGELU ? 2 : 0));
+    const int act = GEN ? p.act : ((EPI == EPI_GELU_PRE || EPI == EPI_GELU_DER) ? 1 : 0);
+    const int aux_mode = GEN ? p.aux_mode : (EPI == EPI_GELU_PRE ? 1 : (EPI == EPI_DGELU ? 2 : (EPI == EPI_GELU_DER ? 4 : (EPI == EPI_MULAUX ? 5 : 0))));
+    const bool aux_store = aux_mode == 1 || aux_mode == 4;                       // the epilogue WRITES aux
+    const bool aux_read = aux_mode == 2 || aux_mode == 3 || aux_mode == 5;       // the epilogue READS aux
     const int out_mode = (GEN || EPI == EPI_F32) ? p.out_mode : (EPI == EPI_ACCUM ? 1 : 0);
-    const bool do_colsum = (GEN || EPI == EPI_DGELU) && p.colsum != nullptr;
+    const bool do_colsum = (GEN || EPI == EPI_DGELU || EPI == EPI_MULAUX) && p.colsum != nullptr;
     const bool use_alpha = (GEN || EPI == EPI_F32) && p.alpha != 1.0f;
     const int esz = out_f32 ? 4 : 2;
     const bool out_vec_ok = (((uintptr_t)p.out & 15) == 0) && ((p.ldo * esz) % 16 == 0);
@@ -417,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const __nv_bfloat16* pre_src = nullptr;          // bf16 tile the epilogue has to READ: saved pre-activation, or the old gradient
     long long pre_ld = 0;
     if (!out_f32) {
-      if (aux_mode >= 2) { pre_src = p.aux; pre_ld = p.ld_aux; }
+      if (aux_read) { pre_src = p.aux; pre_ld = p.ld_aux; }
       else if (out_mode == 1) { pre_src = reinterpret_cast<const __nv_bfloat16*>(p.out); pre_ld = p.ldo; }
     }
     const bool pre_vec_ok = pre_src != nullptr && (pre_ld & 7) == 0 && ((uintptr_t)pre_src & 15) == 0;
@@ -461,7 +470,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint4 pre[8];
       auto group_fast = [&](int gI) {
         const int col0 = tn * BN + half * kColsPerWarp + gI * 64;
-        return rows_full && col0 + 64 <= p.N && out_vec_ok && (pre_src == nullptr || pre_vec_ok) && (aux_mode != 1 || aux_vec_ok);
+        return rows_full && col0 + 64 <= p.N && out_vec_ok && (pre_src == nullptr || pre_vec_ok) && (!aux_store || aux_vec_ok);
       };
       auto issue_pre = [&](int gI) {
         if (!group_fast(gI)) return;
@@ -501,13 +510,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           }
-          if (aux_mode == 1) {
-            // also emit the pre-activation (needed by the dGELU / dReLU backward)
+          if (aux_store) {
+            // also emit the pre-activation (needed by the dGELU / dReLU backward) -- or, mode 4, the derivative itself
+            if (aux_mode == 4) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) =
+                    make_uint4(pack_bf16(dgelu_erf(v[c * 8]), dgelu_erf(v[c * 8 + 1])), pack_bf16(dgelu_erf(v[c * 8 + 2]), dgelu_erf(v[c * 8 + 3])),
+                               pack_bf16(dgelu_erf(v[c * 8 + 4]), dgelu_erf(v[c * 8 + 5])), pack_bf16(dgelu_erf(v[c * 8 + 6]), dgelu_erf(v[c * 8 + 7])));
+            } else {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) =
                   make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]), pack_bf16(v[c * 8 + 4], v[c * 8 + 5]),
                              pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+            }
             __syncwarp();
             if (fast) {
               __nv_bfloat16* ap = p.aux + (long long)(row0 + r_sub) * p.ld_aux + col0 + c_sub * 8;
@@ -522,8 +539,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
             __syncwarp();
-          } else if (aux_mode >= 2) {
-            // the aux tile (pre-activation saved by the forward) goes through smem so that every lane gets its own row
+          } else if (aux_read) {
+            // the aux tile (pre-activation / derivative saved by the forward) goes through smem so that every lane gets its own row
             if (fast) {
 #pragma unroll
               for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(stg + stage_off(it * 4 + r_sub, c_sub)) = pre[it];
@@ -542,7 +559,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
               const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[c * 8 + j] = aux_mode == 2 ? v[c * 8 + j] * dgelu_erf(a[j]) : (a[j] > 0.f ? v[c * 8 + j] : 0.f);
+              for (int j = 0; j < 8; ++j)
+                v[c * 8 + j] = aux_mode == 2 ? v[c * 8 + j] * dgelu_erf(a[j]) : (aux_mode == 5 ? v[c * 8 + j] * a[j] : (a[j] > 0.f ? v[c * 8 + j] : 0.f));
             }
             __syncwarp();
           }
@@ -621,7 +639,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           }
           __syncwarp();
-          if (aux_mode < 2 && pre_src != nullptr && gI + 1 < kGroups) issue_pre(gI + 1);   // RMW: old values of the next group
+          if (!aux_read && pre_src != nullptr && gI + 1 < kGroups) issue_pre(gI + 1);   // RMW: old values of the next group
         }
       } else {
         // ---------------- fp32 output: groups of 32 columns (128-byte row segment) ----------------
@@ -868,7 +886,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   p.colsum = a.colsum;
   HAMT_REQUIRE(a.colsum == nullptr || (!a.out_f32 && a.out_mode == 0), "gemm: colsum needs a plainly stored bf16 output");
   HAMT_REQUIRE(p.aux_mode == 0 || p.aux != nullptr, "gemm: aux_mode set without aux buffer");
-  HAMT_REQUIRE(!(p.aux_mode >= 2 && p.out_mode != 0), "gemm: the dGELU / dReLU epilogues store, they do not accumulate");
+  HAMT_REQUIRE(p.aux_mode >= 0 && p.aux_mode <= 5, "gemm: unknown aux_mode");
+  HAMT_REQUIRE(!((p.aux_mode == 2 || p.aux_mode == 3 || p.aux_mode == 5) && p.out_mode != 0), "gemm: the dGELU / dReLU / multiply epilogues store, they do not accumulate");
+  HAMT_REQUIRE(p.aux_mode != 4 || p.act == 1, "gemm: aux_mode 4 stores gelu'(pre-activation) and needs act = gelu");
 
   CUtensorMap ta, tb;
   int rc;
@@ -884,7 +904,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   else if (p.alpha == 1.0f) {
     if (p.act == 0 && p.aux_mode == 0 && p.colsum == nullptr) epi = p.out_mode == 0 ? EPI_STORE : (p.out_mode == 1 ? EPI_ACCUM : EPI_GENERIC);
     else if (p.act == 1 && p.aux_mode == 1 && p.out_mode == 0 && p.colsum == nullptr) epi = EPI_GELU_PRE;
+    else if (p.act == 1 && p.aux_mode == 4 && p.out_mode == 0 && p.colsum == nullptr) epi = EPI_GELU_DER;
     else if (p.act == 0 && p.aux_mode == 2 && p.out_mode == 0) epi = EPI_DGELU;
+    else if (p.act == 0 && p.aux_mode == 5 && p.out_mode == 0) epi = EPI_MULAUX;
   }
   // 16-warp epilogue for the dGELU dgrad: fully aligned problems only (no guards in epilogue_wide)
   if (g_wide_epi && bn == 256 && epi == EPI_DGELU) {
@@ -906,12 +928,14 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   if (!a.a_mn && !a.b_mn) {                                                                          \
     if (epi == EPI_STORE) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_STORE)                           \
     if (epi == EPI_GELU_PRE) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_GELU_PRE)                     \
+    if (epi == EPI_GELU_DER) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_GELU_DER)                     \
     if (epi == EPI_F32) HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_F32)                               \
     HAMT_LAUNCH(BN_, false, false, PAIR_, EPI_GENERIC)                                               \
   }                                                                                                  \
   if (!a.a_mn && a.b_mn) {                                                                           \
     if (epi == EPI_STORE) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_STORE)                            \
     if (epi == EPI_DGELU) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_DGELU)                            \
+    if (epi == EPI_MULAUX) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_MULAUX)                          \
     if (epi == EPI_ACCUM) HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_ACCUM)                            \
     HAMT_LAUNCH(BN_, false, true, PAIR_, EPI_GENERIC)                                                \
   }                                                                                                  \

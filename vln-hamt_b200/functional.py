@@ -42,6 +42,25 @@ def _as32(x16: torch.Tensor, x32: Optional[torch.Tensor]) -> torch.Tensor:
 # data-parallel hook) and at the end of the backward pass.  HAMT_WGRAD_STREAM=0 restores the single-stream order.
 WGRAD_SIDE_STREAM = os.environ.get("HAMT_WGRAD_STREAM", "1") != "0"
 _side_streams = {}
+# Text branch on its own stream (vilmodel.NavPreTrainedModel.forward): the 9 text layers (M = 5 120: short, latency-bound launches at
+# about half the tensor-pipe rate of the panorama GEMMs) are independent of the history / observation embedders (panorama encoder,
+# M = 34 560) until the cross-modal layers, forward and backward.  On separate streams the block scheduler interleaves their CTAs, so
+# the fill / drain bubbles of the short kernels are covered by the long ones.  autograd runs each backward node on its forward's
+# stream and orders cross-stream gradients itself.
+BRANCH_STREAMS = os.environ.get("HAMT_BRANCH_STREAMS", "0") != "0"
+_branch_streams = {}
+
+
+def branch_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _branch_streams.get(key)
+    if st is None:
+        st = _branch_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _is_branch_stream(st) -> bool:
+    return any(st == b for b in _branch_streams.values())
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
@@ -73,15 +92,16 @@ class Run:
 
     def fork_wgrad(self, fn, *keep):
         """Run fn() (a weight-gradient GEMM) on the side stream, ordered after everything enqueued so far on the current stream."""
-        if not WGRAD_SIDE_STREAM:
-            fn()
-            return
         cur = torch.cuda.current_stream()
+        if not WGRAD_SIDE_STREAM or _is_branch_stream(cur):
+            fn()            # (a branch stream is already off the critical path: its weight gradients stay in stream order)
+            return
         side = _side_stream(cur.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             fn()
         self._side = side
+        self._fork_stream = cur     # the operands kept below were allocated on this stream: it is the one that must wait before they go
         self._side_refs.append(keep)
         self._refs_total += 1
         if not self._join_queued:
@@ -95,9 +115,15 @@ class Run:
         if hook is not None and layer is not None:
             hook(layer)
 
+    def _wait_targets(self):
+        cur = torch.cuda.current_stream()
+        fs = getattr(self, "_fork_stream", None)
+        return [cur] if (fs is None or fs == cur) else [cur, fs]
+
     def _retire(self, mark):
         ev, total, layer = mark
-        torch.cuda.current_stream().wait_event(ev)
+        for st in self._wait_targets():
+            st.wait_event(ev)
         del self._side_refs[:total - self._refs_base]
         self._refs_base = total
         self._hook(layer)           # the layer's weight gradients are final: data-parallel exchange may start
@@ -105,7 +131,8 @@ class Run:
     def join_side(self):
         """Main stream waits for all forked weight-gradient work; pending layer hooks fire."""
         if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)
+            for st in self._wait_targets():
+                st.wait_stream(self._side)
             self._side = None
             self._side_refs.clear()
             self._refs_base = self._refs_total
@@ -209,8 +236,9 @@ def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None, x32=None, y32_out=Non
     A = run.arena
     w1, w2 = inter.dense.weight, out_mod.dense.weight
     if run.save:
+        # h = gelu'(pre-activation), evaluated by the forward epilogue next to gelu itself: the backward epilogue is one multiply
         h = torch.empty((x.shape[0], w1.shape[0]), dtype=BF16, device=x.device)
-        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=h)
+        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU, aux=h)
     else:
         h = None
         a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU)
@@ -231,7 +259,7 @@ def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
     dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(out_mod.dense.bias), drop=d_hid, dres_out=dx_out)
     _wgrad(run, dt, a, w2)
     b1 = inter.dense.bias
-    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h,
+    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL, aux=h,
                   colsum=A.grad(b1) if (b1 is not None and b1.requires_grad) else None)     # bias gradient fused into the dgrad epilogue
     _wgrad(run, dh, x, w1)
     ops.gemm(dh, A.w16(w1), b_mn=True, out=dx, accumulate=True)
@@ -733,7 +761,7 @@ class VitFn(torch.autograd.Function):
             y2, _, z1, x32, mean1, rstd1 = ops.ln_fwd_prenorm(t, x32, blk.norm2.weight, blk.norm2.bias, eps, d1, save=run.save)
             d_mid = run.drop(mlp.drop)
             h = torch.empty((N * S, mlp.fc1.weight.shape[0]), dtype=BF16, device=images.device) if run.save else None
-            a = ops.gemm(y2, A.w16(mlp.fc1.weight), bias=mlp.fc1.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE if run.save else ops.AUX_NONE, aux=h)
+            a = ops.gemm(y2, A.w16(mlp.fc1.weight), bias=mlp.fc1.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU if run.save else ops.AUX_NONE, aux=h)
             m_mid = None
             if d_mid.p > 0:        # Mlp.drop between GELU and fc2 (:148): mask from the device hash, applied as an elementwise pass
                 m_mid = _post_drop_mask(a.view(-1, E), d_mid).view_as(a)
@@ -770,12 +798,9 @@ class VitFn(torch.autograd.Function):
             # ---- mlp sublayer (+ the LayerNorm that followed it)
             dt2, g_x = ops.ln_bwd(g_y, z2, mean2, rstd2, nn_.weight, A.grad(nn_.weight), A.grad(nn_.bias), A.grad(mlp.fc2.bias), dres_in=g_x, drop=d2, prenorm=True)
             _wgrad(run, dt2, a, mlp.fc2.weight)
-            if m_mid is None:
-                dh = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=A.grad(mlp.fc1.bias))
-            else:
-                da = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True)
-                dh = _mul_dact(da * m_mid, h, ops.AUX_MUL_DGELU)
-                ops.colsum(dh, A.grad(mlp.fc1.bias))
+            # h holds gelu'(pre-activation) (forward epilogue); with Mlp.drop active the keep-mask is folded into it
+            hd = h if m_mid is None else h * m_mid
+            dh = ops.gemm(dt2, A.w16(mlp.fc2.weight), b_mn=True, aux_mode=ops.AUX_MUL, aux=hd, colsum=A.grad(mlp.fc1.bias))
             _wgrad(run, dh, y2, mlp.fc1.weight)
             g_y = ops.gemm(dh, A.w16(mlp.fc1.weight), b_mn=True)
             # ---- attention sublayer (+ norm2)

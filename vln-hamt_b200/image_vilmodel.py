@@ -45,9 +45,14 @@ class NavImagePreTrainedModel(NavPreTrainedModel):
         return f.detach() if detach else f
 
     def forward(self, txt_ids, txt_masks, hist_images, hist_ang_feats, hist_pano_images, hist_pano_ang_feats, hist_masks,
-                ob_images, ob_ang_feats, ob_nav_types, ob_masks, hist_mrc_masks=None, ob_v_exists=None):
-        """image_vilmodel.py:61-123."""
-        run = self.begin()
+                ob_images, ob_ang_feats, ob_nav_types, ob_masks, hist_mrc_masks=None, ob_v_exists=None, _run=None):
+        """image_vilmodel.py:61-123.  Feature tensors ([B,T,F] / [B,T,P,F] / [B,O,F]) in the image slots take the feature path of the
+        parent class unchanged (the pretraining heads call it that way after `MultiStepNavImagePreTraining` ran the backbone)."""
+        is_feat = lambda t, nd: t is None or t.dim() == nd      # noqa: E731
+        if is_feat(hist_images, 3) and is_feat(hist_pano_images, 4) and is_feat(ob_images, 3):
+            return super().forward(txt_ids, txt_masks, hist_images, hist_ang_feats, hist_pano_images, hist_pano_ang_feats, hist_masks,
+                                   ob_images, ob_ang_feats, ob_nav_types, ob_masks, _run=_run)
+        run = _run or self.begin()
         B = txt_ids.shape[0]
         hist_img_feats = hist_pano_img_feats = None
         if hist_images is not None:

@@ -42,7 +42,7 @@ class Drop:
 NO_DROP = Drop(None, 0, 0.0)
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-AUX_NONE, AUX_STORE_PRE, AUX_MUL_DGELU, AUX_MUL_DRELU = 0, 1, 2, 3
+AUX_NONE, AUX_STORE_PRE, AUX_MUL_DGELU, AUX_MUL_DRELU, AUX_STORE_DGELU, AUX_MUL = 0, 1, 2, 3, 4, 5
 
 
 def _check_bf16_2d(t: torch.Tensor, name: str):
