@@ -538,7 +538,7 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "value": round(samples * world / (ms * 1e-3), 1), "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms / args.steps, 3),
-                              "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "clocks": clocks}), flush=True)
+                              "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "grad_wire": args.grad_wire, "clocks": clocks}), flush=True)
         if world > 1:
             if trainer is not None:
                 trainer.steps.clear()          # captured graphs hold NCCL work: destroy_process_group hangs while they are alive

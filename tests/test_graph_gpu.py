@@ -179,10 +179,14 @@ def test_run_to_run_gradient_drift_is_bounded():
     g4 = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
     assert torch.equal(l1, l2) and torch.equal(l3, l4) and torch.equal(l1, l3)
     assert g1.keys() == g2.keys() == g3.keys() == g4.keys()
-    worst = 0.0
+    # (gradients that are identically zero in exact arithmetic -- the key bias of every attention: rows of dS sum to zero -- are pure
+    # rounding noise, so the drift is measured against the larger of the tensor's own norm and 1e-3 of the typical gradient norm)
+    norms = sorted(g1[k].float().norm().item() for k in g1)
+    floor = 1e-3 * norms[len(norms) // 2]
+    report = []
     for k in g1:
-        n = g1[k].float().norm().item()
-        for other in (g2, g3, g4):
-            d = (other[k].float() - g1[k].float()).norm().item() / max(n, 1e-20)
-            worst = max(worst, d)
-    assert worst <= 2e-5, worst
+        n = max(g1[k].float().norm().item(), floor)
+        d = max((other[k].float() - g1[k].float()).norm().item() / n for other in (g2, g3, g4))
+        report.append((d, k))
+    report.sort(reverse=True)
+    assert report[0][0] <= 2e-5, report[:6]

@@ -100,6 +100,16 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// gelu(x) and gelu'(x) together: one Gaussian tail (ex2) shared by both, one more ex2 for the density
+__device__ __forceinline__ void gelu_and_derivative(float x, float& g, float& d) {
+  const float a = fabsf(x);
+  const float p = gauss_tail(a);
+  g = fmaf(-a, p, fmaxf(x, 0.f));
+  const float cdf = x >= 0.f ? 1.0f - p : p;
+  const float e = ex2_approx(x * x * -0.72134752044448170368f);
+  d = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 // ---------------------------------------------------------------------------------------------
 // dropout: stateless counter hash.  keep(idx) is a pure function of (seed, site, idx) so forward
 // and backward regenerate the identical mask without storing it.  `seed` lives in device memory

@@ -42,25 +42,12 @@ def _as32(x16: torch.Tensor, x32: Optional[torch.Tensor]) -> torch.Tensor:
 # data-parallel hook) and at the end of the backward pass.  HAMT_WGRAD_STREAM=0 restores the single-stream order.
 WGRAD_SIDE_STREAM = os.environ.get("HAMT_WGRAD_STREAM", "1") != "0"
 _side_streams = {}
-# Text branch on its own stream (vilmodel.NavPreTrainedModel.forward): the 9 text layers (M = 5 120: short, latency-bound launches at
-# about half the tensor-pipe rate of the panorama GEMMs) are independent of the history / observation embedders (panorama encoder,
-# M = 34 560) until the cross-modal layers, forward and backward.  On separate streams the block scheduler interleaves their CTAs, so
-# the fill / drain bubbles of the short kernels are covered by the long ones.  autograd runs each backward node on its forward's
-# stream and orders cross-stream gradients itself.
-BRANCH_STREAMS = os.environ.get("HAMT_BRANCH_STREAMS", "0") != "0"
-_branch_streams = {}
-
-
-def branch_stream(device) -> "torch.cuda.Stream":
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    st = _branch_streams.get(key)
-    if st is None:
-        st = _branch_streams[key] = torch.cuda.Stream(device=device)
-    return st
-
-
-def _is_branch_stream(st) -> bool:
-    return any(st == b for b in _branch_streams.values())
+# (Measured and removed in round 2: running the text branch -- embedder + 9 text layers, M = 5 120 -- on its own stream next to the
+# panorama encoder, forward and backward.  The CTAs of the two branches interleave, but every kernel of the path is a persistent grid
+# that wants all 148 SMs: 11.18 ms/step against 10.95 without; profiles/r02_ab_streams.txt.)
+# FFN blocks: save gelu'(pre) in the forward epilogue and multiply by it in the dgrad epilogue (1) or save the pre-activation and evaluate
+# the derivative in the dgrad epilogue (0, the round-1 pair) -- A/B switch, default by measurement (profiles/r02_ab_streams.txt, r02_kbench_ffn_epilogues.txt)
+GELU_DERIVATIVE = os.environ.get("HAMT_GELU_DER", "1") != "0"
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
@@ -104,9 +91,12 @@ class Run:
         self._fork_stream = cur     # the operands kept below were allocated on this stream: it is the one that must wait before they go
         self._side_refs.append(keep)
         self._refs_total += 1
+        self._ensure_final_join()
+
+    def _ensure_final_join(self):
+        """(backward pass only) final join at the end of this backward pass (heads / embedders have no layer hook); inside a captured
+        step this is also what re-joins the forked streams before the capture ends."""
         if not self._join_queued:
-            # final join at the end of this backward pass (heads / embedders have no layer hook); inside a captured step this is
-            # also what re-joins the forked branch before the capture ends
             self._join_queued = True
             torch.autograd.Variable._execution_engine.queue_callback(self._final_join)
 
@@ -143,6 +133,9 @@ class Run:
     def _final_join(self):
         self._join_queued = False
         self.join_side()
+        bs = getattr(self, "_branch", None)
+        if bs is not None:          # the text branch's backward ran on its own stream: nothing else orders it before what follows the step
+            torch.cuda.current_stream().wait_stream(bs)
 
     def used(self, layer):
         self.uses[id(layer)] = self.uses.get(id(layer), 0) + 1
@@ -238,7 +231,7 @@ def ffn_block_fwd(run: Run, x, inter, out_mod, y_out=None, x32=None, y32_out=Non
     if run.save:
         # h = gelu'(pre-activation), evaluated by the forward epilogue next to gelu itself: the backward epilogue is one multiply
         h = torch.empty((x.shape[0], w1.shape[0]), dtype=BF16, device=x.device)
-        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU, aux=h)
+        a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU if GELU_DERIVATIVE else ops.AUX_STORE_PRE, aux=h)
     else:
         h = None
         a = ops.gemm(x, A.w16(w1), bias=inter.dense.bias, act=ops.ACT_GELU)
@@ -259,7 +252,7 @@ def ffn_block_bwd(run: Run, dy, saved, inter, out_mod, dx_out=None):
     dt, dx = ops.ln_bwd(dy, z, mean, rstd, ln.weight, A.grad(ln.weight), A.grad(ln.bias), A.grad(out_mod.dense.bias), drop=d_hid, dres_out=dx_out)
     _wgrad(run, dt, a, w2)
     b1 = inter.dense.bias
-    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL, aux=h,
+    dh = ops.gemm(dt, A.w16(w2), b_mn=True, aux_mode=ops.AUX_MUL if GELU_DERIVATIVE else ops.AUX_MUL_DGELU, aux=h,
                   colsum=A.grad(b1) if (b1 is not None and b1.requires_grad) else None)     # bias gradient fused into the dgrad epilogue
     _wgrad(run, dh, x, w1)
     ops.gemm(dh, A.w16(w1), b_mn=True, out=dx, accumulate=True)
@@ -552,6 +545,7 @@ class TextEmbedFn(torch.autograd.Function):
     def backward(ctx, dy):
         A, emb = ctx.run.arena, ctx.emb
         dy = dy.to(BF16).contiguous()
+        ctx.run._ensure_final_join()
         ctx.run.join_side()         # the tied MLM decoder's weight gradient (side stream) lands in the word-embedding gradient too
         ops.embed_text_bwd(dy, ctx.ids, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
                            emb.LayerNorm.weight, A.grad(emb.word_embeddings.weight), A.grad(emb.position_embeddings.weight),

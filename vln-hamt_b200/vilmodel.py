@@ -420,21 +420,8 @@ class NavPreTrainedModel(HamtPreTrainedModel):
 
     # ---- encoder -----------------------------------------------------------------------------
     def _text_branch(self, run, txt_ids, B, L, txt_mask):
-        """Text embedder + text layers; with Fn.BRANCH_STREAMS on their own stream (forked where the history / observation embedders
-        were ENQUEUED, i.e. before them in stream order: the fork point is an event recorded at begin-of-forward)."""
-        fork = getattr(run, "_fork_event", None)
-        if not Fn.BRANCH_STREAMS or fork is None:
-            return self._text_layers(run, self._text(run, txt_ids), B, L, txt_mask)
-        cur = torch.cuda.current_stream()
-        bs = Fn.branch_stream(txt_ids.device)
-        bs.wait_event(fork)
-        with torch.cuda.stream(bs):
-            txt, txt32 = self._text_layers(run, self._text(run, txt_ids), B, L, txt_mask)
-        cur.wait_stream(bs)
-        for t in (txt, txt32):
-            if t is not None:
-                t.record_stream(cur)
-        return txt, txt32
+        """Text embedder + text layers."""
+        return self._text_layers(run, self._text(run, txt_ids), B, L, txt_mask)
 
     def _text_layers(self, run, txt, B, L, txt_mask):
         """-> (txt bf16, txt32: its fp32 twin from the last LayerNorm, or None without layers)."""
@@ -460,9 +447,6 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         H = self.config.hidden_size
         txt_mask = _additive_mask(txt_masks)
         hist_mask = _additive_mask(hist_masks)
-        if Fn.BRANCH_STREAMS:
-            run._fork_event = torch.cuda.Event()
-            run._fork_event.record()
         cls = self._hist_cls(run, B)
         if hist_img_feats is not None:
             T = hist_img_feats.shape[1]
@@ -515,9 +499,6 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         R = 1 + num_neg_trajs
         txt_mask = _additive_mask(txt_masks)
         hist_mask = _additive_mask(hist_masks)
-        if Fn.BRANCH_STREAMS:
-            run._fork_event = torch.cuda.Event()
-            run._fork_event.record()
         cls = self._hist_cls(run, B).view(B, 1, H)
         nopos = self._hist_steps(run, hist_img_feats, hist_ang_feats, hist_pano_img_feats, hist_pano_ang_feats, with_pos=False).view(B, T, H)
         # text side after the history embedder (see forward(): backward order / gradient-exchange overlap)
