@@ -80,8 +80,8 @@ class Run:
     def fork_wgrad(self, fn, *keep):
         """Run fn() (a weight-gradient GEMM) on the side stream, ordered after everything enqueued so far on the current stream."""
         cur = torch.cuda.current_stream()
-        if not WGRAD_SIDE_STREAM or _is_branch_stream(cur):
-            fn()            # (a branch stream is already off the critical path: its weight gradients stay in stream order)
+        if not WGRAD_SIDE_STREAM:
+            fn()
             return
         side = _side_stream(cur.device)
         side.wait_stream(cur)
@@ -133,9 +133,6 @@ class Run:
     def _final_join(self):
         self._join_queued = False
         self.join_side()
-        bs = getattr(self, "_branch", None)
-        if bs is not None:          # the text branch's backward ran on its own stream: nothing else orders it before what follows the step
-            torch.cuda.current_stream().wait_stream(bs)
 
     def used(self, layer):
         self.uses[id(layer)] = self.uses.get(id(layer), 0) + 1
