@@ -185,6 +185,8 @@ def test_run_to_run_gradient_drift_is_bounded():
     floor = 1e-3 * norms[len(norms) // 2]
     report = []
     for k in g1:
+        if k.endswith("key.bias") or k == "next_action.net.4.bias":     # identically zero: rows of dS / of (softmax - onehot) sum to zero
+            continue
         n = max(g1[k].float().norm().item(), floor)
         d = max((other[k].float() - g1[k].float()).norm().item() / n for other in (g2, g3, g4))
         report.append((d, k))

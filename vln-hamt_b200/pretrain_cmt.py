@@ -195,7 +195,10 @@ class MultiStepNavCMTPreTraining(HamtPreTrainedModel):
         txt_embeds, hist_embeds, ob_embeds = self.bert(txt_ids, txt_masks, hist_img_fts, hist_ang_fts, hist_pano_img_fts, hist_pano_ang_fts,
                                                        hist_masks, ob_img_fts, ob_ang_fts, ob_nav_types, ob_masks, _run=run)
         B, O, H = ob_embeds.shape
-        anchor_ob_embeds = torch.gather(ob_embeds, 1, sp_anchor_idxs.unsqueeze(1).unsqueeze(2).repeat(1, 36, H))
+        # reference: torch.gather(ob_embeds, 1, anchor.unsqueeze(1).unsqueeze(2).repeat(1, 36, H)) (pretrain_cmt.py:202) -- the same values
+        # as one row per sample broadcast over the 36 views; written this way the backward is a 36-way sum + a collision-free row
+        # scatter instead of gather's bf16 atomic scatter_add (order-dependent rounding: the only run-to-run noise above fp32 level)
+        anchor_ob_embeds = ob_embeds[torch.arange(B, device=ob_embeds.device), sp_anchor_idxs].unsqueeze(1).expand(B, 36, H)
         cat_ob_embeds = torch.cat([anchor_ob_embeds, ob_embeds[:, :-1]], -1)                   # (batch, 36, 2H)
         prediction_scores = self.sprel_head._run(run, cat_ob_embeds.reshape(B * 36, 2 * H)).view(B, 36, 2)
         if compute_loss:
