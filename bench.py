@@ -748,9 +748,9 @@ def main():
             gbs = w / us / 1e3
             hbm_rooflines.append({"kernel": name, "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(gbs / peaks["hbm"], 3),
                                   "launches": n, "share_of_step": round(us * 1e-3 / n_prof / step_ms, 3), "traffic": None})
-    # DRAM bytes per launch of the most expensive GEMM signature, from the committed ncu --set full capture (profiles/r01_traffic.json)
+    # DRAM bytes per launch of the most expensive GEMM signature, from the committed ncu --set full capture (profiles/r02_traffic.json)
     traffic, traffic_of = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(tp):
         tj = json.load(open(tp))
         traffic, traffic_of = tj.get("dram_bytes_per_launch"), {"signature": tj.get("signature"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"), "source": tj.get("source")}

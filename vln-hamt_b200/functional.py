@@ -35,7 +35,7 @@ def _as32(x16: torch.Tensor, x32: Optional[torch.Tensor]) -> torch.Tensor:
 # Weight-gradient GEMMs on a second stream.  dW = dY^T X only feeds the gradient buffer: nothing later in the backward pass reads
 # it, while the dgrad GEMM that consumes the same dY is on the critical path.  Every GEMM is a persistent grid holding all 148 SMs
 # (one ~200 KB CTA each), so two dependent launches never overlap: the measured cost of a launch is ~8 us on top of its
-# tensor-pipe time (pipeline fill, last-tile epilogue, grid drain; profiles/r02_bench_signatures_g.txt, intercept of time against
+# tensor-pipe time (pipeline fill, last-tile epilogue, grid drain; profiles/r02_bench_signatures_final.txt, intercept of time against
 # K at M = 5120) and there are ~260 GEMM launches per step.  With the wgrads forked onto a side stream the block scheduler places
 # their CTAs on the SMs the critical-path kernel frees while it drains (and vice versa), in eager mode and -- as parallel
 # branches -- inside the captured step graph.  The side stream is joined where a layer's gradients must be final (Run.done:
