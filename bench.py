@@ -330,6 +330,8 @@ def main():
     ap.add_argument("--nccl-sms", type=int, default=-1,
                     help="N > 1: SMs the backward GEMMs leave free for the overlapped NCCL all-reduce kernels (= NCCL channel cap); "
                          "-1 = default (0 = no reservation)")
+    ap.add_argument("--nccl-channels", type=int, default=0, help="N > 1: cap NCCL's channel count (= CTAs of the all-reduce kernel) without reserving SMs; 0 = NCCL default")
+    ap.add_argument("--nccl-high-prio", action="store_true", help="N > 1: NCCL on a high-priority stream (measured at N = 2: no gain, profiles/r02_scale_n2.txt)")
     ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
                     help="N > 1: dtype of the gradient all-reduce on the wire (bf16 = opt-in compressed exchange, unmeasured; default fp32 like DDP)")
     ap.add_argument("--no-store-leg", action="store_true", help="skip the second e2e variant (device-resident FeatureStore, indices from the host)")
@@ -374,7 +376,15 @@ def main():
         if nccl_sms > 0:     # the all-reduce kernel gets exactly the SMs the backward GEMMs leave free
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_sms))
             os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nccl_sms))
-        dist.init_process_group("nccl", device_id=dev)
+        if args.nccl_channels > 0:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
+        pg_opts = None
+        if args.nccl_high_prio:
+            try:
+                pg_opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:  # noqa: BLE001 -- older torch: keep the default stream priority
+                pg_opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
     conf = CONFIGS[args.config]
     schedule = args.tasks.split(",") if args.tasks else conf["schedule"]
     SHAPE = conf["shape"]
@@ -538,7 +548,8 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "value": round(samples * world / (ms * 1e-3), 1), "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms / args.steps, 3),
-                              "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "grad_wire": args.grad_wire, "clocks": clocks}), flush=True)
+                              "nccl_sms": nccl_sms, "dp_mode": args.dp_mode, "grad_wire": args.grad_wire, "nccl_channels": args.nccl_channels,
+                              "nccl_high_priority_stream": args.nccl_high_prio, "clocks": clocks}), flush=True)
         if world > 1:
             if trainer is not None:
                 trainer.steps.clear()          # captured graphs hold NCCL work: destroy_process_group hangs while they are alive
@@ -771,7 +782,8 @@ def main():
                        "l2": "no explicit flush: each step streams ~10 GB of activations + 1.4 GB of weights/grads, >> 126 MB L2",
                        "grad_exchange": ("layer-overlapped all_reduce(AVG) on flat fp32 grads" if overlap else
                                          ("all_reduce(AVG) on the flat fp32 grad slices, " + ("captured at the end of the step graph" if in_graph and use_graphs else "after backward")))
-                       if world > 1 else "none", "nccl_sms_reserved_in_backward": nccl_sms, "grad_wire_dtype": args.grad_wire},
+                       if world > 1 else "none", "nccl_sms_reserved_in_backward": nccl_sms, "grad_wire_dtype": args.grad_wire,
+                       "nccl_high_priority_stream": args.nccl_high_prio if world > 1 else None},
             "gpu_launches": int(launches),
             "model_tflops": round(alg_flops_per_step * args.steps / (ms * 1e-3) / 1e12 * 1.0, 1),
             "clocks": clocks,

@@ -68,7 +68,10 @@ def main():
         print(json.dumps(row), flush=True)
     # attention (pano / text / cross / vision shapes of the batch-64 step, plus the 16-token history-only shapes of MLM / MRC / ITM)
     from hamt_b200 import _lib
-    for (B, Sq, Sk) in [(960, 36, 36), (64, 80, 80), (64, 80, 53), (64, 53, 80), (64, 53, 53), (64, 16, 80), (64, 80, 16), (64, 16, 16), (2560, 36, 36)]:
+    shapes_attn = [(960, 36, 36), (64, 80, 80), (64, 80, 53), (64, 53, 80), (64, 53, 53), (64, 16, 80), (64, 80, 16), (64, 16, 16), (2560, 36, 36)]
+    if "--attn-long" in sys.argv:       # RxR instructions (L = 300) and the ViT sequence (S = 197): legacy kernels (key axis > 128)
+        shapes_attn = [(64, 300, 300), (64, 300, 58), (64, 58, 300), (82, 197, 197)]
+    for (B, Sq, Sk) in shapes_attn:
       for legacy in ((1, 2) if "--attn-ab" in sys.argv else (0,)):       # 1 = legacy mma.sync kernels, 2 = tcgen05 forced wherever it fits, 0 = shipped dispatch
         _lib.load().hamt_attn_set_impl(legacy)
         qkv = torch.randn(B * max(Sq, Sk), 2304, device="cuda").to(torch.bfloat16)

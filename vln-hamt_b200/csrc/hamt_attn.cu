@@ -219,7 +219,7 @@ __device__ __forceinline__ void frag_colsum(const float (&acc)[8][4], float* sds
 // LONG = true : long sequences (RxR instructions, L = 300): Q, dO, K, V of the (batch, head) pair fill shared memory, so the dQ
 //               pass RECOMPUTES S and dP from registers (7 instead of 5 small matmuls) and needs no dS buffer; one CTA per SM.
 template <bool LONG>
-__global__ void __launch_bounds__(256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP p) {
+__global__ void __launch_bounds__(LONG ? 384 : 256, LONG ? 1 : 2) attn_bwd_kernel(const AttnP p) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem[];
   const int Sq_pad = (p.Sq + 15) & ~15, Sk_pad = (p.Sk + 15) & ~15;
@@ -526,7 +526,9 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   }
   int nw = (Sk_pad > Sq_pad ? Sk_pad : Sq_pad) / 16;
   if (nw > 8) nw = 8;
-  if (is_long) launch_pdl(attn_bwd_kernel<true>, a.f.B * a.f.heads, 256, smem, st, p);
+  // LONG: one CTA per SM (Q, dO, K, V of the pair fill shared memory): 12 warps, so the 19 key / query tiles of an RxR instruction
+  // (L = 300) take two rounds per phase instead of three
+  if (is_long) launch_pdl(attn_bwd_kernel<true>, a.f.B * a.f.heads, 384, smem, st, p);
   else launch_pdl(attn_bwd_kernel<false>, a.f.B * a.f.heads, nw * 32, smem, st, p);
   return check_launch("attn_bwd_kernel");
 }
