@@ -251,3 +251,21 @@ def test_gemm_wide_dgelu_epilogue_matches_8warp_epilogue(M, tile_n):
     assert (base[1] - wide[1]).abs().max().item() <= 1e-3 * max(1.0, base[1].abs().max().item())
     ref = (dy.float() @ w2.float()) * _dgelu_ref(pre.float())
     assert (wide[0].float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_mlm_decoder_shapes_row_tiles_fastest_and_splitk_dgrad():
+    """Tied MLM decoder (pretrain_cmt.py:96-99, vilmodel.py:280-284): logits [n, 30522] = x [n, 768] W^T with a 47 MB weight (row tiles
+    iterate fastest so that it is read once) and its dgrad dx [n, 768] = dlogits [n, 30522] W (split-K into fp32)."""
+    ops = _ops()
+    M, N, K = 804, 30522, 768
+    x, w = _rand((M, K), 31), _rand((N, K), 32, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(33)).cuda() * 0.1
+    out = torch.empty((M, (N + 7) // 8 * 8), dtype=torch.float32, device="cuda")[:, :N]
+    ops.gemm(x, w, bias=bias, out=out, out_dtype=torch.float32)
+    ref = x.float() @ w.float().t() + bias
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-4
+    dl = torch.zeros((M, (N + 7) // 8 * 8), dtype=torch.bfloat16, device="cuda")
+    dl[:, :N] = _rand((M, N), 34, 0.01)
+    dx = ops.gemm(dl[:, :N], w, b_mn=True, out_dtype=torch.float32, accumulate=True)
+    refd = dl[:, :N].float() @ w.float()
+    assert (dx - refd).abs().max().item() <= 2e-3 * refd.abs().max().item() + 1e-4

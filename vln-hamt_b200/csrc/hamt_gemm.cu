@@ -33,6 +33,9 @@ static constexpr int kThreads = 64 + kEpiThreads;
 struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  int m_fast;         // work-unit order: 0 = column tiles fastest (CTAs of a wave share the A rows; the usual case: few column tiles, weights
+                      // resident in L2), 1 = row tiles fastest (few row tiles and a B operand larger than L2's share: the MLM decoder,
+                      // 804 x 30522 x 768 -- with columns fastest its 47 MB weight was re-read from HBM once per row tile)
   void* out;
   long long ldo;
   int out_f32;        // 0: bf16 out, 1: fp32 out
@@ -123,8 +126,8 @@ __device__ __forceinline__ void epilogue_wide(const GemmParams& p, uint8_t* stag
   int as = 0;
   uint32_t aphase = 0;
   for (int u = u_first; u < units; u += u_stride) {
-    const int tn = u % p.tiles_n;
-    const int tm = (u / p.tiles_n) % p.tiles_m;
+    const int tn = p.m_fast ? (u / p.tiles_m) % p.tiles_n : u % p.tiles_n;
+    const int tm = p.m_fast ? u % p.tiles_m : (u / p.tiles_n) % p.tiles_m;
     if (has_bias) {
       if (et < BN) sbias[as * BN + et] = __ldg(p.bias + tn * BN + et);
       epi_bar_sync<kET>();
@@ -304,8 +307,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int u = u_first; u < units; u += u_stride) {
-        const int tn = u % p.tiles_n;
-        const int tm = (u / p.tiles_n) % p.tiles_m;
+        const int tn = p.m_fast ? (u / p.tiles_m) % p.tiles_n : u % p.tiles_n;
+        const int tm = p.m_fast ? u % p.tiles_m : (u / p.tiles_n) % p.tiles_m;
         const int sp = u / (p.tiles_n * p.tiles_m);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -437,8 +440,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     constexpr int kGroups = (BN / 2) / 64;
 
     for (int u = u_first; u < units; u += u_stride) {
-      const int tn = u % p.tiles_n;
-      const int tm = (u / p.tiles_n) % p.tiles_m;
+      const int tn = p.m_fast ? (u / p.tiles_m) % p.tiles_n : u % p.tiles_n;
+      const int tm = p.m_fast ? u % p.tiles_m : (u / p.tiles_n) % p.tiles_m;
       if (has_bias) {   // stage this tile's bias slice (double-buffered by accumulator stage)
         if (et < BN) sbias[as * BN + et] = (tn * BN + et < p.N) ? __ldg(p.bias + tn * BN + et) : 0.f;
         epi_bar_sync();
@@ -898,6 +901,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.m_fast = (p.tiles_m < p.tiles_n && p.tiles_m <= 16 && (long long)a.N * a.K * 2 > (32ll << 20)) ? 1 : 0;
   p.out = a.out; p.ldo = a.ldo; p.out_f32 = a.out_f32;
   p.out_mode = (a.out_mode == 2 && p.splits == 1) ? 1 : a.out_mode;
   p.bias = a.bias; p.act = a.act; p.aux_mode = a.aux_mode; p.aux = (__nv_bfloat16*)a.aux; p.ld_aux = a.ld_aux;

@@ -459,7 +459,14 @@ class LinearFn(torch.autograd.Function):
             dy = _mul_dact(dy, pre, ops.AUX_MUL_DRELU)
         _wgrad(run, dy, x, weight)
         _bgrad(A, dy, bias)
-        dx = ops.gemm(dy, A.w16(weight), b_mn=True) if ctx.need_dx else None
+        dx = None
+        if ctx.need_dx:
+            if weight.shape[0] >= 8192 and dy.shape[0] <= 2048:
+                # tied MLM decoder (pretrain_cmt.py:96-99): reduction over 30 522 classes with only ~20 output tiles -- split-K into an
+                # fp32 scratch (red.global.add) and one small cast instead of 21 CTAs walking 477 k-blocks each (122 us -> ~30 us)
+                dx = ops.gemm(dy, A.w16(weight), b_mn=True, out_dtype=F32, accumulate=True).to(BF16)
+            else:
+                dx = ops.gemm(dy, A.w16(weight), b_mn=True)
         ctx.x = ctx.pre = None
         return None, dx, None, None, None, None, None, None
 
