@@ -192,3 +192,50 @@ def test_run_to_run_gradient_drift_is_bounded():
         report.append((d, k))
     report.sort(reverse=True)
     assert report[0][0] <= 2e-5, report[:6]
+
+
+def test_itm_device_negative_sampling_distribution_and_graph_capture():
+    """config.itm_device_negatives: negatives and position shuffles drawn on the device with the distribution of the
+    reference's host loops (vilmodel.py:676-704): a negative is never the sample itself and is uniform over the others; a shuffle is a
+    permutation of the valid history steps followed by the padding positions in order.  Inside a captured step the draws are fresh on
+    every replay (no host plan in the batch)."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200 import graph, synth
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    from hamt_b200.vilmodel import itm_negative_plan_device
+    torch.manual_seed(0)
+    B, T = 6, 9
+    lens = torch.tensor([9, 1, 4, 7, 2, 9])
+    hm = (torch.arange(T + 1)[None] < (lens + 1)[:, None]).cuda()
+    counts = torch.zeros(B, B)
+    for _ in range(200):
+        neg, shuf = itm_negative_plan_device(B, hm, T, 4)
+        assert neg.shape == (B, 2) and len(shuf) == 2
+        assert (neg != torch.arange(B, device="cuda")[:, None]).all() and neg.min() >= 0 and neg.max() < B
+        for j in range(2):
+            counts[torch.arange(B), neg[:, j].cpu()] += 1
+        for s in shuf:
+            s = s.cpu()
+            for i in range(B):
+                n = int(lens[i])
+                assert sorted(s[i, :n].tolist()) == list(range(n)) and s[i, n:].tolist() == list(range(n, T))
+    off = counts[~torch.eye(B, dtype=torch.bool)]
+    assert counts.diag().sum() == 0 and off.min() > 0.5 * off.mean() and off.max() < 1.6 * off.mean()      # 400 draws per row over 5 others
+    # captured ITM step without a host plan: replays draw new negatives
+    model = MultiStepNavCMTPreTraining(HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1, itm_device_negatives=True))
+    model.load_state_dict(synth.seeded_state_dict(model, seed=3))
+    model = model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    b = synth.make_batch("itm", seed=1, batch_size=4, txt_len=24, hist_len=5)
+    bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    bd["_itm_device_negatives"] = True
+    trainer = graph.GraphedTrainer(model)
+    e = graph.add_sync_free_extras("itm", bd)
+    assert "itm_plan" not in e
+    losses = [trainer.step("itm", e).detach().float().clone() for _ in range(4)]
+    torch.cuda.synchronize()
+    assert len(trainer.steps) == 1 and all(torch.isfinite(l).all() for l in losses)
+    assert any(not torch.equal(losses[0], l) for l in losses[1:])

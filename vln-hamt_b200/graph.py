@@ -39,7 +39,7 @@ def add_sync_free_extras(task: str, batch: Dict, device=None) -> Dict:
         m = b[src]
         mask = (m != skip) if skip is not None else m
         b[key] = torch.nonzero(mask.reshape(-1), as_tuple=False).squeeze(1)
-    if task == "itm":
+    if task == "itm" and not b.get("_itm_device_negatives", False):       # (config.itm_device_negatives: the step draws them on the device)
         hm = b.get("_hist_masks_host")           # host copy kept next to a device-resident batch: no device->host sync
         if hm is None:
             hm = b["hist_masks"].cpu()

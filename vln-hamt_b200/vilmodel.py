@@ -345,6 +345,30 @@ def itm_negative_plan(batch_size: int, hist_masks: torch.Tensor, hist_max_len: i
     return neg_idxs, shuffled
 
 
+def itm_negative_plan_device(batch_size: int, hist_masks: torch.Tensor, hist_max_len: int, num_neg_trajs: int = 4):
+    """Device-side negative sampling for forward_itm: the same DISTRIBUTION as itm_negative_plan -- K in-batch negatives
+    per sample, uniform over the other samples with replacement (np.random.choice's default), and K position shuffles, each a uniform
+    permutation of the sample's valid history steps followed by the padding positions in order -- drawn with torch's CUDA generator,
+    no host loop, no host sync, capturable in the step graph (fresh draws on every replay).  Not the reference's RNG STREAM: opt-in
+    through `config.itm_device_negatives`; the default keeps the host plan so that the draws match the reference call for call."""
+    dev = hist_masks.device
+    K = num_neg_trajs // 2
+    neg_idxs = None
+    if batch_size > 1:
+        r = torch.randint(0, batch_size - 1, (batch_size, K), device=dev)
+        neg_idxs = r + (r >= torch.arange(batch_size, device=dev).unsqueeze(1)).long()          # skip the sample itself
+    else:
+        K = num_neg_trajs
+    lens = hist_masks.long().sum(1, keepdim=True) - 1                                            # valid steps (CLS slot excluded)
+    pos = torch.arange(hist_max_len, device=dev).unsqueeze(0).expand(batch_size, -1)
+    shuffled = []
+    for _ in range(K):
+        keys = torch.rand(batch_size, hist_max_len, device=dev)
+        keys = torch.where(pos < lens, keys, 2.0 + pos.float())                                  # padding keeps its place behind the valid steps
+        shuffled.append(torch.argsort(keys, dim=1))
+    return neg_idxs, shuffled
+
+
 def _additive_mask(mask: torch.Tensor) -> torch.Tensor:
     """(1 - m) * -10000 as an fp32 row per sample (vilmodel.py:597-599); the kernels add it after the 1/sqrt(d) scale."""
     return ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
@@ -527,7 +551,9 @@ class NavPreTrainedModel(HamtPreTrainedModel):
         dev = txt_ids.device
         hist = h_layers(torch.cat([cls, with_pos(torch.arange(T, device=dev).expand(B, -1))], 1))
         neg_embeds, neg_masks = [], []
-        if _plan is None:
+        if _plan is None and getattr(self.config, "itm_device_negatives", False):
+            _plan = itm_negative_plan_device(B, hist_masks, T, num_neg_trajs)
+        elif _plan is None:
             _plan = itm_negative_plan(B, hist_masks, T, num_neg_trajs)      # host RNG draws in the reference's order (+1 host sync)
             _plan = (None if _plan[0] is None else _plan[0].to(dev), [t.to(dev) for t in _plan[1]])
         neg_idxs, shuffled = _plan
