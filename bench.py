@@ -331,7 +331,7 @@ def main():
                     help="N > 1: SMs the backward GEMMs leave free for the overlapped NCCL all-reduce kernels (= NCCL channel cap); "
                          "-1 = default (0 = no reservation)")
     ap.add_argument("--nccl-channels", type=int, default=0, help="N > 1: cap NCCL's channel count (= CTAs of the all-reduce kernel) without reserving SMs; 0 = NCCL default")
-    ap.add_argument("--nccl-high-prio", action="store_true", help="N > 1: NCCL on a high-priority stream (measured at N = 2: no gain, profiles/r02_scale_n2.txt)")
+    ap.add_argument("--nccl-high-prio", action="store_true", help="N > 1: NCCL on a high-priority stream (measured at N = 2: no gain, profiles/r02_scale.txt)")
     ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
                     help="N > 1: dtype of the gradient all-reduce on the wire (bf16 = opt-in compressed exchange, unmeasured; default fp32 like DDP)")
     ap.add_argument("--no-store-leg", action="store_true", help="skip the second e2e variant (device-resident FeatureStore, indices from the host)")
