@@ -14,7 +14,9 @@ dt, w2 = t(M, 768), t(768, 3072)
 cs = torch.zeros(3072, device="cuda")
 cases = [("plain", lambda: ops.gemm(x, w1, bias=b1)),
          ("gelu", lambda: ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_PRE, aux=h)),
-         ("dgelu", lambda: ops.gemm(dt, w2, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=cs))]
+         ("dgelu", lambda: ops.gemm(dt, w2, b_mn=True, aux_mode=ops.AUX_MUL_DGELU, aux=h, colsum=cs)),
+         ("gelu+derivative (round 2)", lambda: ops.gemm(x, w1, bias=b1, act=ops.ACT_GELU, aux_mode=ops.AUX_STORE_DGELU, aux=h)),
+         ("mul-aux (round 2)", lambda: ops.gemm(dt, w2, b_mn=True, aux_mode=ops.AUX_MUL, aux=h, colsum=cs))]
 for _ in range(2):
     for name, fn in cases:
         fn(); torch.cuda.synchronize()

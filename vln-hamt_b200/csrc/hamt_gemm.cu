@@ -903,7 +903,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t st) {
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.m_fast = (p.tiles_m < p.tiles_n && p.tiles_m <= 16 && (long long)a.N * a.K * 2 > (32ll << 20)) ? 1 : 0;
   p.out = a.out; p.ldo = a.ldo; p.out_f32 = a.out_f32;
-  p.out_mode = (a.out_mode == 2 && p.splits == 1) ? 1 : a.out_mode;
+  // fp32 accumulation keeps the fire-and-forget red.global.add even without a K split: the read-modify-write epilogue waits for its loads
+  // (tied MLM decoder wgrad, 30522 x 768 x 804: 124 us with RMW at splits = 1 against 76 us with red at splits = 2,
+  // profiles/r02_kbench_decoder.txt)
+  p.out_mode = a.out_mode;
   p.bias = a.bias; p.act = a.act; p.aux_mode = a.aux_mode; p.aux = (__nv_bfloat16*)a.aux; p.ld_aux = a.ld_aux;
   p.alpha = a.alpha;
   p.colsum = a.colsum;
