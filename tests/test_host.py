@@ -215,3 +215,43 @@ def test_optimizer_host_side_grouping_and_validation():
         optim.AdamW(arena, list(model.parameters()), betas=(1.0, 0.9))
     with pytest.raises(ValueError, match="invalid optimizer"):
         optim.build_optimizer(model, SimpleNamespace(optim="rangerlars", learning_rate=1e-4, betas=[0.9, 0.98], weight_decay=0.0))
+
+
+def test_itm_device_negative_plan_properties_on_cpu():
+    """The device-side ITM sampler is device-agnostic torch code: same support as the reference's host loops (vilmodel.py:676-704)."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200.vilmodel import itm_negative_plan_device
+    torch.manual_seed(1)
+    B, T = 5, 7
+    lens = torch.tensor([7, 1, 3, 6, 2])
+    hm = torch.arange(T + 1)[None] < (lens + 1)[:, None]
+    for _ in range(50):
+        neg, shuf = itm_negative_plan_device(B, hm, T, 4)
+        assert neg.shape == (B, 2) and (neg != torch.arange(B)[:, None]).all() and 0 <= int(neg.min()) and int(neg.max()) < B
+        assert len(shuf) == 2
+        for s in shuf:
+            for i in range(B):
+                n = int(lens[i])
+                assert sorted(s[i, :n].tolist()) == list(range(n)) and s[i, n:].tolist() == list(range(n, T))
+    neg1, shuf1 = itm_negative_plan_device(1, hm[:1], T, 4)          # batch of one: no in-batch negatives, four shuffles (vilmodel.py:684-686)
+    assert neg1 is None and len(shuf1) == 4
+
+
+def test_image_pretraining_model_state_dict_layout():
+    """End-to-end stage: `bert.vision_backbone.*` comes first (registered first in image_vilmodel.py:25) with timm's key names,
+    followed by exactly the keys of the feature model; everything lives in ONE arena."""
+    import hamt_b200  # noqa: F401
+    from hamt_b200.config import HamtConfig
+    from hamt_b200.image_pretrain import MultiStepNavImagePreTraining
+    from hamt_b200.pretrain_cmt import MultiStepNavCMTPreTraining
+    cfg = HamtConfig(num_l_layers=1, num_x_layers=1, num_h_pano_layers=1)
+    img = MultiStepNavImagePreTraining(cfg, vit_depth=2)
+    feat = MultiStepNavCMTPreTraining(cfg)
+    ki, kf = list(img.state_dict().keys()), list(feat.state_dict().keys())
+    vit = [k for k in ki if k.startswith("bert.vision_backbone.")]
+    assert ki[:len(vit)] == vit and ki[len(vit):] == kf
+    assert vit[:4] == ["bert.vision_backbone.cls_token", "bert.vision_backbone.pos_embed", "bert.vision_backbone.patch_embed.proj.weight",
+                       "bert.vision_backbone.patch_embed.proj.bias"]
+    assert "bert.vision_backbone.blocks.1.attn.qkv.weight" in vit and "bert.vision_backbone.norm.bias" in vit
+    assert img.bert.vision_backbone.arena() is img.arena() and img.bert.arena() is img.arena()
+    assert tuple(img.state_dict()["bert.vision_backbone.patch_embed.proj.weight"].shape) == (768, 3, 16, 16)
